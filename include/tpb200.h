@@ -1,0 +1,195 @@
+/* tpb200.h - C ABI of libtpb200.so, the B200-native hot path of thermalporous.
+ *
+ * The reference (tlroy/thermalporous) is pure Python on Firedrake/PETSc; its hot path is
+ * everything that runs inside one `self.solver.solve()` (thermalporous/thermalmodel.py:165):
+ * residual + Jacobian assembly of the DG0/TPFA forms (singlephase.py:60-273,
+ * twophase.py:67-411), the PC set-up (preconditioners.py:875-878, 1545-1548) and the
+ * CPR/CPTR-preconditioned (F)GMRES solve driven by SNES newtonls.  Each entry point below
+ * names the reference interface it stands in for.  A maintainer of the reference binds
+ * these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - all pointers are raw addresses; `on_device` arguments say whether they are host or
+ *     CUDA device addresses (device pointers must belong to the handle's device).
+ *   - fp64 everywhere.  cell index c = i + nx*(j + ny*k) over the LOCAL slab.
+ *   - state / vectors are field-major SoA: v[f*ncell + c], f in (p, T) or (p, T, S_o)
+ *     (the field order of twophase.py:99 and of Firedrake's mixed-space aij matrix).
+ *   - Jacobian values use the block-stencil layout J[((s*nf + r)*nf + c)*ncell + cell],
+ *     s in (diag, x-, x+, y-, y+, z-, z+); entries that would leave the domain are 0.
+ *   - every function returns 0 on success or a negative TPB_ERR_*; solver outcomes are
+ *     reported in `reason` fields using PETSc's numbering (KSP/SNESConvergedReason).
+ *   - one host thread per handle; all work is queued on the handle's CUDA stream;
+ *     functions that return scalars synchronise that stream.
+ */
+#ifndef TPB200_H
+#define TPB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPB_OK 0
+#define TPB_ERR_ARG (-1)
+#define TPB_ERR_CUDA (-2)
+#define TPB_ERR_STATE (-3)
+#define TPB_ERR_UNSUPPORTED (-4)
+#define TPB_ERR_NCCL (-5)
+
+typedef struct tpb_handle_s* tpb_handle;
+
+/* structured grid of the local slab: rectanglegeo.py:28-34 (2-D), boxgeo.py:31-44 (3-D).
+ * dim == 2 => nz must be 1.  Slabs are cut along the slowest axis (z in 3-D, y in 2-D). */
+typedef struct {
+    int dim;
+    int nx, ny, nz;      /* local owned cells */
+    double dx, dy, dz;
+    int has_lo, has_hi;  /* 1 if another rank owns the plane below / above this slab */
+} tpb_grid;
+
+/* physicalparameters.py:9-35 (only what the forms read) */
+typedef struct {
+    double ko, kw, kr;
+    double c_v_w, c_v_o, c_r, rho_r;
+    double T_inj, T_prod;
+    double API;
+    double g;
+    double S_o;          /* initial saturation: enters p_weight/o_weight, twophase.py:144-147 */
+    double U;            /* heater coefficient, physicalparameters.py:29 */
+    int gravity;         /* 1: 3-D forms carry g (always, twophase.py:317); 0 for tests */
+} tpb_params;
+
+enum tpb_field { TPB_PHI = 0, TPB_KX = 1, TPB_KY = 2, TPB_KZ = 3, TPB_KT = 4 };
+enum tpb_source_kind { TPB_PROD = 0, TPB_INJ = 1, TPB_HEATER = 2 };
+
+/* one (cell, kind) source entry = one non-zero of a reference delta Function times the cell
+ * volume (wellcase.py:110-169, heatercase.py:80-118, sourceterms.py:86-153).
+ * Rates follow wellcase.py:171-266 / sourceterms.py:155-269. */
+typedef struct {
+    int64_t cell;        /* local cell index */
+    int32_t kind;        /* tpb_source_kind */
+    int32_t const_rate;  /* constant_rate=True: rate = max_rate */
+    double weight;       /* V_cell * delta(cell) */
+    double bhp;
+    double max_rate;     /* < 0 for producers (wellcase.py:100) */
+} tpb_source;
+
+/* ---- solver option surface: singlephase.py:275-444, twophase.py:413-1002 ---------------- */
+enum tpb_ksp_type { TPB_KSP_GMRES = 0, TPB_KSP_FGMRES = 1 };
+enum tpb_stage1 {
+    TPB_S1_NONE = 0,          /* pc_ilu / pc_bilu: second stage only */
+    TPB_S1_CPR = 1,           /* CPRStage1PC, preconditioners.py:335-906 */
+    TPB_S1_CPTR = 2,          /* CPTRStage1PC, preconditioners.py:1243-1571 (two-phase) */
+    TPB_S1_FIELDSPLIT = 3     /* single-phase pc_fieldsplit_*: Schur FULL on (p | T), no stage 2 */
+};
+enum tpb_decoup { TPB_DECOUP_NO = 0, TPB_DECOUP_QI = 1, TPB_DECOUP_TI = 2,
+                  TPB_DECOUP_QI_TEMP = 3, TPB_DECOUP_TI_TEMP = 4 };
+enum tpb_schur_pre { TPB_SCHUR_CONVDIFF = 0,  /* ConvDiffSchur(TwoPhases)PC, preconditioners.py:11-333 */
+                     TPB_SCHUR_A11 = 1,       /* pc_fieldsplit_schur_precondition a11 */
+                     TPB_SCHUR_DIAG = 2 };    /* pc_fieldsplit_diag: additive, no coupling */
+enum tpb_stage2 { TPB_S2_NONE = 0, TPB_S2_ILU0 = 1, TPB_S2_BJACOBI = 2 };
+
+typedef struct {
+    /* SNES newtonls */
+    int snes_max_it;          /* 15 single-phase (singlephase.py:293), 25 two-phase (twophase.py:424) */
+    double snes_rtol, snes_atol, snes_stol;  /* PETSc defaults 1e-8, 1e-50, 1e-8 */
+    int linesearch;           /* 0 basic (full step), 1 backtracking (PETSc default `bt`) */
+    /* KSP */
+    int ksp_type;             /* tpb_ksp_type */
+    int ksp_max_it, ksp_restart;   /* 200, 200 */
+    double ksp_rtol, ksp_atol;     /* 1e-5 (gmres default) | 1e-8 (twophase.py:432) */
+    /* PC tree */
+    int stage1, decoup, schur_pre, stage2;
+    /* pressure / temperature multigrid V-cycle standing in for BoomerAMG (v_cycle dict) */
+    int mg_pre, mg_post;      /* smoothing sweeps (red-black Gauss-Seidel) */
+    int mg_coarse_sweeps;
+    int mg_min_cells;         /* stop coarsening below this many cells */
+    double mg_overcorrection; /* scaling of the piecewise-constant coarse correction */
+    int mg_cycles;            /* V-cycles per application (pc_hypre_boomeramg_max_iter) */
+    /* second stage: ILU(0) over tiles (block-Jacobi of ILU(0) blocks, as PETSc bjacobi+ilu) */
+    int ilu_tile[3];
+    int verbose;
+} tpb_solver_opts;
+
+typedef struct {
+    int nits;                 /* snes.getIterationNumber(), thermalmodel.py:327 */
+    int lits;                 /* snes.getLinearSolveIterations(), thermalmodel.py:328 */
+    int reason;               /* SNESConvergedReason numbering: >0 converged, <0 diverged */
+    int nfev;                 /* residual evaluations (line search included) */
+    double fnorm0, fnorm;
+    double t_assemble_ms, t_pcsetup_ms, t_ksp_ms, t_total_ms;  /* CUDA-event timings */
+} tpb_stats;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* replaces: model construction on a geo (singlephase.py:7-50, twophase.py:8-55). nphase 1|2. */
+int tpb_create(const tpb_grid* grid, int nphase, const tpb_params* prm, int device, tpb_handle* out);
+int tpb_destroy(tpb_handle h);
+const char* tpb_last_error(tpb_handle h);
+int tpb_version(void);
+
+/* replaces: geo.phi/K_x/K_y/K_z/kT Functions (SPE10model3D.py:26-72, homogeneousboxgeo.py:10-19).
+ * `data` has ncell doubles.  lo/hi: the neighbour ranks' boundary planes (may be NULL when
+ * has_lo/has_hi is 0; tpb_exchange_static fills them over NCCL instead). */
+int tpb_set_field(tpb_handle h, int field, const double* data, int on_device);
+int tpb_set_field_ghost(tpb_handle h, int field, const double* lo, const double* hi, int on_device);
+/* replaces: case.prod_wells / inj_wells / heaters / deltas_* (wellcase.py, heatercase.py, sourceterms.py) */
+int tpb_set_sources(tpb_handle h, int n, const tpb_source* src);
+
+/* ---- assembly (K1/K2): replaces assemble(F), assemble(J) inside SNES (thermalmodel.py:36,165) -- */
+/* u, u_old: nf*ncell; F: nf*ncell; J (optional, may be NULL): ns*nf*nf*ncell, all device. */
+int tpb_assemble(tpb_handle h, const double* u, const double* u_old, double dt, double* F, double* J);
+/* ghost planes of the state for multi-rank slabs (nf*nplane each, device); NULL keeps previous */
+int tpb_set_state_ghost(tpb_handle h, const double* u_lo, const double* u_hi);
+size_t tpb_jacobian_size(tpb_handle h);   /* number of doubles in J */
+int tpb_nstencil(tpb_handle h);
+
+/* ---- SpMV (K9): replaces PETSc MatMult on the aij Jacobian ------------------------------- */
+int tpb_spmv(tpb_handle h, const double* J, const double* x, double* y);
+
+/* ---- preconditioner (K3-K8): replaces PCSetUp / PCApply of the composite tree -------------- */
+int tpb_solver_defaults(int nphase, tpb_solver_opts* o);
+int tpb_set_solver_opts(tpb_handle h, const tpb_solver_opts* o);
+/* J: Jacobian to precondition; u: state it was assembled at (frozen coefficients of the
+ * ConvDiff Schur operator, appctx["state"], preconditioners.py:24,178); dt as in assembly */
+int tpb_pc_setup(tpb_handle h, const double* J, const double* u, double dt);
+int tpb_pc_apply(tpb_handle h, const double* x, double* y);
+
+/* ---- Krylov (K10): replaces KSPSolve (gmres right-PC | fgmres) ----------------------------- */
+int tpb_ksp_solve(tpb_handle h, const double* J, const double* b, double* x, int* its, int* reason,
+                  double* rnorm);
+
+/* ---- Newton (K11 + A9): replaces NonlinearVariationalSolver.solve() (thermalmodel.py:165) -- */
+/* u: in = initial guess, out = solution (device, nf*ncell); u_old device. */
+int tpb_newton_solve(tpb_handle h, double* u, const double* u_old, double dt, tpb_stats* stats);
+/* same, but u / u_old are HOST buffers: copies in, solves, copies the solution back */
+int tpb_newton_solve_host(tpb_handle h, double* u_host, const double* u_old_host, double dt, tpb_stats* stats);
+
+/* ---- small reductions used by the time loop (thermalmodel.py:190-229) ---------------------- */
+/* out[0]=min S, out[1]=max S over field f of u */
+int tpb_field_minmax(tpb_handle h, const double* u, int f, double* out);
+int tpb_clip_field(tpb_handle h, double* u, int f, double lo, double hi);
+int tpb_dot(tpb_handle h, const double* x, const double* y, size_t n, double* out);
+
+/* ---- multi-GPU: slab partition; NCCL is loaded at run time (dlopen of libnccl.so.2) -------- */
+/* nccl_unique_id: the 128-byte ncclUniqueId made by rank 0 and broadcast by the caller */
+int tpb_comm_init(tpb_handle h, const void* nccl_unique_id, int rank, int nranks);
+int tpb_comm_unique_id(void* out128);
+int tpb_exchange_static(tpb_handle h);   /* ghost planes of phi,K*,kT after tpb_set_field */
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+/* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
+int64_t tpb_launch_count(tpb_handle h);
+/* timing of the dominant kernels with CUDA events on the handle's stream: runs `reps` launches
+ * of kernel `which` (0 assemble F+J, 1 assemble F, 2 spmv) and returns the mean ms per launch */
+int tpb_time_kernel(tpb_handle h, int which, const double* u, const double* u_old, double dt,
+                    double* F, double* J, const double* x, double* y, int reps, double* ms);
+void* tpb_stream(tpb_handle h);
+/* block the calling host thread until everything queued on the handle's stream is done */
+int tpb_sync(tpb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

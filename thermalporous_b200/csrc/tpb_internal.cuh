@@ -1,0 +1,321 @@
+// tpb_internal.cuh - shared declarations of libtpb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "tpb200.h"
+
+#define TPB_MAXF 3
+
+struct tpb_exception {
+    int code;
+    std::string msg;
+};
+
+#define TPB_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            throw tpb_exception{TPB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)}; \
+        }                                                                                \
+    } while (0)
+
+#define TPB_REQUIRE(cond, code, text)            \
+    do {                                         \
+        if (!(cond)) throw tpb_exception{code, text}; \
+    } while (0)
+
+// geometry of the local slab, passed by value to kernels
+struct Geom {
+    int dim, nx, ny, nz;
+    int np;          // cells per plane of the slab axis (nx*ny in 3-D, nx in 2-D)
+    int nl;          // planes in the slab (nz in 3-D, ny in 2-D)
+    int has_lo, has_hi;
+    long long n;     // owned cells
+    double h[3];     // centre distances Dx, Dy, Dz
+    double area[3];  // facet measure per axis
+    double vol;
+};
+
+// physical constants in device form
+struct DevParams {
+    double ko, kw, kr, c_v_w, c_v_o, c_r, rho_r, T_inj, T_prod, U;
+    double g;            // 0 when gravity is off or dim == 2
+    double Wp, Wo;       // p_weight, o_weight (twophase.py:144-147)
+    // oil_rho / oil_mu coefficients (physicalparameters.py:37-57)
+    double rho_ref, mu_o_pref, mu_o_exp;
+};
+
+// a cell field plus the two ghost planes of the slab axis
+struct GField {
+    const double* v;
+    const double* lo;
+    const double* hi;
+};
+
+__host__ __device__ inline int tpb_ns(int dim) { return dim == 3 ? 7 : 5; }
+
+// ---------------------------------------------------------------------------------------------
+// forward-mode dual numbers (value + N partials); everything is unrolled into registers
+// ---------------------------------------------------------------------------------------------
+template <int N>
+struct Dual {
+    double v;
+    double d[N > 0 ? N : 1];
+};
+
+template <int N>
+__device__ __forceinline__ Dual<N> dconst(double a) {
+    Dual<N> r;
+    r.v = a;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = 0.0;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dvar(double a, int slot) {
+    Dual<N> r;
+    r.v = a;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = (i == slot) ? 1.0 : 0.0;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator+(const Dual<N>& a, const Dual<N>& b) {
+    Dual<N> r;
+    r.v = a.v + b.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = a.d[i] + b.d[i];
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(const Dual<N>& a, const Dual<N>& b) {
+    Dual<N> r;
+    r.v = a.v - b.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = a.d[i] - b.d[i];
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(const Dual<N>& a) {
+    Dual<N> r;
+    r.v = -a.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = -a.d[i];
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) {
+    Dual<N> r;
+    r.v = a.v * b.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator*(double s, const Dual<N>& a) {
+    Dual<N> r;
+    r.v = s * a.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = s * a.d[i];
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator*(const Dual<N>& a, double s) { return s * a; }
+template <int N>
+__device__ __forceinline__ Dual<N> operator+(const Dual<N>& a, double s) {
+    Dual<N> r = a;
+    r.v += s;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(const Dual<N>& a, double s) {
+    Dual<N> r = a;
+    r.v -= s;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(double s, const Dual<N>& a) {
+    Dual<N> r;
+    r.v = s - a.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = -a.d[i];
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
+    Dual<N> r;
+    double ib = 1.0 / b.v;
+    r.v = a.v * ib;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+    return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator/(double s, const Dual<N>& b) {
+    Dual<N> r;
+    double ib = 1.0 / b.v;
+    r.v = s * ib;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = -r.v * b.d[i] * ib;
+    return r;
+}
+// place a Dual<M> into slots [OFF, OFF+M) of a Dual<N>
+template <int N, int OFF, int M>
+__device__ __forceinline__ Dual<N> dembed(const Dual<M>& a) {
+    Dual<N> r;
+    r.v = a.v;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.d[i] = (i >= OFF && i < OFF + M) ? a.d[(i - OFF) < M ? (i - OFF) : 0] : 0.0;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// properties with partials w.r.t. (p, T); physicalparameters.py:37-98
+// ---------------------------------------------------------------------------------------------
+// oil_rho = rho_ref * e^{5.5e-5 (10 p - 1.01325)} * e^{-2.5e-4 (T - 288.7056)}   (:37-46)
+__device__ __forceinline__ void oil_rho_d(const DevParams& P, double p, double T, double& r, double& r_p,
+                                          double& r_T) {
+    r = P.rho_ref * exp(5.5e-5 * (p * 10.0 - 1.01325) - 2.5e-4 * (T - (15.5556 + 273.15)));
+    r_p = 5.5e-4 * r;
+    r_T = -2.5e-4 * r;
+}
+__device__ __forceinline__ double oil_rho_v(const DevParams& P, double p, double T) {
+    return P.rho_ref * exp(5.5e-5 * (p * 10.0 - 1.01325) - 2.5e-4 * (T - (15.5556 + 273.15)));
+}
+// 1/oil_mu, oil_mu = 1e-3 * 10^{A1 API + A2} * Tf^{A3 API + A4}, Tf = 1.8 (T - 273.15) + 32   (:48-57)
+__device__ __forceinline__ void oil_imu_d(const DevParams& P, double T, double& im, double& im_T) {
+    double Tf = 1.8 * (T - 273.15) + 32.0;
+    double mu = P.mu_o_pref * pow(Tf, P.mu_o_exp);
+    im = 1.0 / mu;
+    im_T = -im * P.mu_o_exp * 1.8 / Tf;  // d(1/mu)/dT = -(1/mu) * exp * Tf'/Tf
+}
+// water_rho: Trangenstein/Kell (:69-82), Tc = T - 272.15
+__device__ __forceinline__ void water_rho_d(double p, double T, double& r, double& r_p, double& r_T) {
+    const double E0 = 999.83952, E1 = 16.955176, E2 = -7.987e-3, E3 = -46.170461e-6, E4 = 105.56302e-9,
+                 E5 = -280.54353e-12, E6 = 16.87985e-3, E7 = 10.2, Cw = 3.98854e-4;
+    double Tc = T - 272.15;
+    double poly = E0 + Tc * (E1 + Tc * (E2 + Tc * (E3 + Tc * (E4 + Tc * E5))));
+    double dpoly = E1 + Tc * (2.0 * E2 + Tc * (3.0 * E3 + Tc * (4.0 * E4 + Tc * 5.0 * E5)));
+    double den = 1.0 / (1.0 + E6 * Tc);
+    double ex = exp(Cw * (p - E7));
+    r = poly * ex * den;
+    r_p = Cw * r;
+    r_T = (dpoly - poly * E6 * den) * ex * den;
+}
+__device__ __forceinline__ double water_rho_v(double p, double T) {
+    double r, a, b;
+    water_rho_d(p, T, r, a, b);
+    return r;
+}
+// 1/water_mu, Grabowski (:84-90), Tf = 1.8 (T - 272.15) + 32
+__device__ __forceinline__ void water_imu_d(double T, double& im, double& im_T) {
+    const double Aw = 2.1850, Bw = 0.04012, Cw = 5.1547e-6;
+    double Tf = 1.8 * (T - 272.15) + 32.0;
+    double q = -1.0 + Bw * Tf + Cw * Tf * Tf;
+    im = q / (1e-3 * Aw);
+    im_T = (Bw + 2.0 * Cw * Tf) * 1.8 / (1e-3 * Aw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct ScalarStencil;  // tpb_pc.cu
+struct PcState;
+struct KspState;
+struct CommState;
+
+struct tpb_handle_s {
+    int device = 0;
+    int nphase = 1, nf = 2, ns = 5;
+    Geom g{};
+    DevParams dp{};
+    tpb_params prm{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // static fields: owned + ghost planes
+    double* fld[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* fld_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* fld_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool fld_set[5] = {false, false, false, false, false};
+    // state ghost planes (nf * np each)
+    double* u_lo = nullptr;
+    double* u_hi = nullptr;
+    // generic vector ghost planes for SpMV inputs (nf * np each)
+    double* x_lo = nullptr;
+    double* x_hi = nullptr;
+
+    // sources grouped by cell
+    int nsrc_cells = 0;
+    int64_t* src_cell = nullptr;  // unique cells
+    int* src_off = nullptr;       // CSR offsets into src_ent
+    tpb_source* src_ent = nullptr;
+
+    // reductions
+    double* red_partial = nullptr;   // per-block partials
+    unsigned int* red_counter = nullptr;
+    double* red_out = nullptr;       // device results
+    double* red_host = nullptr;      // pinned host mirror
+    int red_cap = 0;
+
+    tpb_solver_opts opts{};
+    PcState* pc = nullptr;
+    KspState* ksp = nullptr;
+    CommState* comm = nullptr;
+
+    // Newton workspace
+    double* nw_F = nullptr;
+    double* nw_J = nullptr;
+    double* nw_du = nullptr;
+    double* nw_utrial = nullptr;
+    double* nw_Ftrial = nullptr;
+    double* nw_uold = nullptr;
+    double* nw_u = nullptr;
+};
+
+// ---- internal entry points shared between translation units -----------------------------------
+void tpb_launch_assemble(tpb_handle_s* h, const double* u, const double* u_old, double dt, double* F, double* J);
+void tpb_launch_spmv(tpb_handle_s* h, const double* J, const double* x, double* y);
+void tpb_halo_vector(tpb_handle_s* h, const double* x, int nfields, double* lo, double* hi);
+void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count);
+
+// blas-1 (tpb_blas.cu)
+void tpb_axpy(tpb_handle_s* h, size_t n, double a, const double* x, double* y);          // y += a x
+void tpb_axpby(tpb_handle_s* h, size_t n, double a, const double* x, double b, double* y);  // y = a x + b y
+void tpb_waxpy(tpb_handle_s* h, size_t n, double a, const double* x, const double* y, double* w);  // w = a x + y
+void tpb_scale(tpb_handle_s* h, size_t n, double a, double* x);
+void tpb_copy(tpb_handle_s* h, size_t n, const double* x, double* y);
+void tpb_zero(tpb_handle_s* h, size_t n, double* x);
+// k dots <x, Y_j> (Y_j = Y + j*ldy), results in h->red_host[0..k) after sync (global over ranks)
+void tpb_mdot(tpb_handle_s* h, size_t n, const double* x, const double* Y, size_t ldy, int k, double* host_out);
+double tpb_norm2(tpb_handle_s* h, size_t n, const double* x);
+double tpb_dot_sync(tpb_handle_s* h, size_t n, const double* x, const double* y);
+// y -= sum_j c[j] V_j  (c on host)
+void tpb_maxpy(tpb_handle_s* h, size_t n, double* y, const double* V, size_t ldv, int k, const double* c);
+
+// pc / ksp (tpb_pc.cu, tpb_solver.cu)
+void tpb_pc_free(tpb_handle_s* h);
+void tpb_ksp_free(tpb_handle_s* h);
+void tpb_comm_free(tpb_handle_s* h);
+void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double dt);
+void tpb_pc_apply_impl(tpb_handle_s* h, const double* x, double* y);
+void tpb_ksp_solve_impl(tpb_handle_s* h, const double* J, const double* b, double* x, int* its, int* reason,
+                        double* rnorm);
+void tpb_newton_impl(tpb_handle_s* h, double* u, const double* u_old, double dt, tpb_stats* st);
+
+template <typename T>
+inline T* tpb_dalloc(size_t count) {
+    T* p = nullptr;
+    if (count == 0) count = 1;
+    TPB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    return p;
+}
+inline void tpb_dfree(void* p) {
+    if (p) cudaFree(p);
+}
