@@ -89,13 +89,13 @@ enum tpb_decoup { TPB_DECOUP_NO = 0, TPB_DECOUP_QI = 1, TPB_DECOUP_TI = 2,
 enum tpb_schur_pre { TPB_SCHUR_CONVDIFF = 0,  /* ConvDiffSchur(TwoPhases)PC, preconditioners.py:11-333 */
                      TPB_SCHUR_A11 = 1,       /* pc_fieldsplit_schur_precondition a11 */
                      TPB_SCHUR_DIAG = 2 };    /* pc_fieldsplit_diag: additive, no coupling */
-enum tpb_stage2 { TPB_S2_NONE = 0, TPB_S2_ILU0 = 1, TPB_S2_BJACOBI = 2 };
+enum tpb_stage2 { TPB_S2_NONE = 0, TPB_S2_ILU0 = 1, TPB_S2_BJACOBI = 2 /* per-cell block Jacobi */ };
 
 typedef struct {
     /* SNES newtonls */
     int snes_max_it;          /* 15 single-phase (singlephase.py:293), 25 two-phase (twophase.py:424) */
     double snes_rtol, snes_atol, snes_stol;  /* PETSc defaults 1e-8, 1e-50, 1e-8 */
-    int linesearch;           /* 0 basic (full step), 1 backtracking (PETSc default `bt`) */
+    int linesearch;           /* 0 basic (full step; Firedrake default), 1 backtracking */
     /* KSP */
     int ksp_type;             /* tpb_ksp_type */
     int ksp_max_it, ksp_restart;   /* 200, 200 */
@@ -104,12 +104,14 @@ typedef struct {
     int stage1, decoup, schur_pre, stage2;
     /* pressure / temperature multigrid V-cycle standing in for BoomerAMG (v_cycle dict) */
     int mg_pre, mg_post;      /* smoothing sweeps (red-black Gauss-Seidel) */
-    int mg_coarse_sweeps;
-    int mg_min_cells;         /* stop coarsening below this many cells */
+    int mg_coarse_sweeps;     /* red-black sweeps on the coarsest level */
+    int mg_min_cells;         /* stop coarsening at or below this many cells */
     double mg_overcorrection; /* scaling of the piecewise-constant coarse correction */
     int mg_cycles;            /* V-cycles per application (pc_hypre_boomeramg_max_iter) */
-    /* second stage: ILU(0) over tiles (block-Jacobi of ILU(0) blocks, as PETSc bjacobi+ilu) */
-    int ilu_tile[3];
+    double mg_semi_theta;     /* an axis is coarsened on a level only if its mean coupling is at least
+                                 theta * the strongest axis' (0 = always coarsen every axis) */
+    /* second stage: block ILU(0) of the nf x nf block stencil in red-black ordering, one block per
+     * rank as PETSc bjacobi+ilu (the slab couplings to other ranks are dropped) */
     int verbose;
 } tpb_solver_opts;
 

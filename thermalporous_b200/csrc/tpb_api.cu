@@ -268,7 +268,7 @@ int tpb_solver_defaults(int nphase, tpb_solver_opts* o) {
     o->snes_rtol = 1e-8;                          // PETSc SNES defaults (the dicts set none)
     o->snes_atol = 1e-50;
     o->snes_stol = 1e-8;
-    o->linesearch = 1;
+    o->linesearch = 0;                            // Firedrake's NonlinearVariationalSolver default: basic
     o->ksp_type = nphase == 1 ? TPB_KSP_GMRES : TPB_KSP_FGMRES;   // singlephase.py:295, twophase.py:426
     o->ksp_max_it = 200;
     o->ksp_restart = 200;
@@ -280,13 +280,11 @@ int tpb_solver_defaults(int nphase, tpb_solver_opts* o) {
     o->stage2 = TPB_S2_ILU0;
     o->mg_pre = 1;
     o->mg_post = 1;
-    o->mg_coarse_sweeps = 8;
-    o->mg_min_cells = 512;
+    o->mg_coarse_sweeps = 4;
+    o->mg_min_cells = 8;
     o->mg_overcorrection = 1.0;
     o->mg_cycles = 1;
-    o->ilu_tile[0] = 8;
-    o->ilu_tile[1] = 8;
-    o->ilu_tile[2] = 8;
+    o->mg_semi_theta = 0.5;
     o->verbose = 0;
     return TPB_OK;
 }

@@ -120,13 +120,9 @@ class Engine:
     # ------------------------------------------------------------------ solver
     def set_solver_opts(self, **kw):
         for k, v in kw.items():
-            if k == "ilu_tile":
-                for a in range(3):
-                    self.opts.ilu_tile[a] = int(v[a])
-            else:
-                if not hasattr(self.opts, k):
-                    raise KeyError(k)
-                setattr(self.opts, k, v)
+            if not hasattr(self.opts, k):
+                raise KeyError(k)
+            setattr(self.opts, k, v)
         self._chk(self.lib.tpb_set_solver_opts(self.h, C.byref(self.opts)))
 
     def pc_setup(self, J, u, dt):
