@@ -1,0 +1,255 @@
+"""Well / heater source cases - host-side mirror of wellcase.py, heatercase.py,
+wellheatercase.py and sourceterms.py of the reference.
+
+Same constructor arguments, presets and attribute names (prod_wells / inj_wells / heaters lists of
+dicts with 'name', 'bhp', 'location', 'delta', 'max_rate'; deltas_prod / deltas_inj / deltas_heaters
+summed fields for SourceTerms).  A 'delta' here is a NumPy array over the cells (the reference's
+DG0 Function values); `source_entries()` flattens a case into the (cell, kind, weight, bhp,
+max_rate, const_rate) records libtpb200 takes (include/tpb200.h: tpb_source), weight = V_cell*delta.
+
+Documented deviation: when no cell centre lies inside the 0.1 m bump the
+reference falls back to the nearest cell with ties broken by Firedrake's dof numbering
+(utils.py:7-25); here ties go to the lowest cell index.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+PROD, INJ, HEATER = 0, 1, 2
+
+
+class _DeltaMixin:
+    _height = 1.0   # wellcase.py:146, heatercase.py:99;  sourceterms.py:116 uses 0.1
+
+    def _radius(self):
+        return getattr(self.params, "well_radius", 0.1)
+
+    def _centres(self):
+        if getattr(self, "_cc", None) is None:
+            self._cc = self.geo.cell_centres()
+        return self._cc
+
+    def well_delta(self, w):
+        """wellcase.py:157-169: 1/V at the cell whose centre is closest to w."""
+        cc = self._centres()
+        d = np.linalg.norm(cc - np.asarray(w, dtype=np.float64)[None, :self.geo.dim], axis=1)
+        delta = np.zeros(self.geo.ncell)
+        delta[int(np.argmin(d))] = 1.0 / self.geo.cell_volume
+        return delta
+
+    def _bump(self, w, radius):
+        cc = self._centres()
+        r2 = (cc[:, 0] - w[0]) ** 2 + (cc[:, 1] - w[1]) ** 2
+        inside = r2 < radius ** 2
+        if self.geo.dim == 3:
+            inside &= np.abs(cc[:, 2] - w[2]) < self._height
+        delta = np.zeros(self.geo.ncell)
+        if inside.any():
+            delta[inside] = np.exp(-(1.0 / (-r2[inside] + radius ** 2)))
+        return delta
+
+    def well_circle(self, w, radius=None):
+        """wellcase.py:110-123 / :141-155: C-infinity bump at the cell centres, normalised to
+        integrate to 1; nearest-cell delta when it integrates to 0."""
+        delta = self._bump(w, self._radius() if radius is None else radius)
+        normalise = delta.sum() * self.geo.cell_volume
+        if normalise == 0:
+            return self.well_delta(w)
+        return delta / normalise
+
+    well_circle3D = well_circle
+
+
+_PRESETS_2D = {
+    "default": lambda s: ([[0.2 * s.Length, s.Length_y / 2]], [[0.8 * s.Length, s.Length_y / 2]]),
+    "SPE10_60x120": lambda s: ([[140.0, 210.0]], [[265.0, 260.0]]),                       # wellcase.py:30-36
+    "test0": lambda s: ([[2., s.Length_y / 4.], [2., s.Length_y / 2.], [2., 3. * s.Length_y / 4]],
+                        [[s.Length - 2., s.Length_y / 4.], [s.Length - 2., s.Length_y / 2.],
+                         [s.Length - 2., 3. * s.Length_y / 4]]),                           # :37-41
+    "test": lambda s: ([[10., f * s.Length_y] for f in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9)],
+                       [[s.Length - 10., f * s.Length_y] for f in (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9)]),
+    "SPE10_40x40": lambda s: ([[2 * s.geo.Dx, s.Length_y / 4.], [2 * s.geo.Dx, s.Length_y / 2.],
+                               [2 * s.geo.Dx, 3. * s.Length_y / 4]],
+                              [[s.Length - 2 * s.geo.Dx, s.Length_y / 4.], [s.Length - 2 * s.geo.Dx, s.Length_y / 2.],
+                               [s.Length - 2 * s.geo.Dx, 3. * s.Length_y / 4]]),
+}
+
+
+def _large3d(s, zf):
+    """wellcase.py:58-64: 3 rows of 7 points; the last point of the third row repeats (7Lx/8, Ly/4)."""
+    Lx, Ly, Lz = s.Length, s.Length_y, s.Length_z
+    xs = [Lx / 8, Lx / 4, 3 * Lx / 8, Lx / 2, 5 * Lx / 8, 3 * Lx / 4, 7 * Lx / 8]
+    pts = [[x, Ly / 2, Lz * zf] for x in xs] + [[x, Ly / 4, Lz * zf] for x in xs] + \
+          [[x, 3 * Ly / 4, Lz * zf] for x in xs[:-1]] + [[7 * Lx / 8, Ly / 4, Lz * zf]]
+    return pts
+
+
+_PRESETS_3D = {
+    "default": lambda s: ([[s.Length / 2, s.Length_y / 2, s.Length_z * 0.2]],
+                          [[s.Length / 2, s.Length_y / 2, s.Length_z * 0.8]]),             # wellcase.py:55-57
+    "large": lambda s: (_large3d(s, 0.2), _large3d(s, 0.8)),
+}
+
+
+class _CaseBase(_DeltaMixin):
+    def _init_geo(self, params, geo):
+        self.Length = geo.Length
+        self.Length_y = geo.Length_y
+        if geo.dim == 3:
+            self.Length_z = geo.Length_z
+        self.geo = geo
+        self.params = params
+        self._cc = None
+
+    def _preset(self, well_case, prod_points, inj_points):
+        if well_case is not None:
+            table = _PRESETS_2D if self.geo.dim == 2 else _PRESETS_3D
+            if well_case not in table:
+                raise KeyError("unknown well_case %r for a %d-D geo" % (well_case, self.geo.dim))
+            prod_points, inj_points = table[well_case](self)
+        return list(prod_points or []), list(inj_points or [])
+
+
+class WellCase(_CaseBase):
+    """wellcase.py:6-108."""
+
+    def __init__(self, params, geo, well_case=None, prod_points=None, inj_points=None, constant_rate=False):
+        self.name = "Wells"
+        self._init_geo(params, geo)
+        self.wellfunc = "circle"
+        self.constant_rate = bool(constant_rate)
+        prod_points, inj_points = self._preset(well_case, prod_points, inj_points)
+        self.init_wells(prod_points, inj_points, self.wellfunc)
+
+    def init_wells(self, prod_points, inj_points, wellfunc):
+        self.prod_wells, self.inj_wells = [], []
+        self.prodcount = self.injcount = 0
+        for point in prod_points:
+            self.prod_wells.append(self.make_well(point, wellfunc, "prod"))
+        for point in inj_points:
+            self.inj_wells.append(self.make_well(point, wellfunc, "inj"))
+
+    def make_well(self, w, wellfunc, welltype):
+        rate, p_inj, p_prod = self.params.rate, self.params.p_inj, self.params.p_prod
+        delta = self.well_delta(w) if wellfunc == "delta" else self.well_circle(w)
+        if welltype == "prod":
+            name, bhp, max_rate = "prod" + str(self.prodcount), p_prod, -rate      # wellcase.py:97-101
+            self.prodcount += 1
+        else:
+            name, bhp, max_rate = "inj" + str(self.injcount), p_inj, rate
+            self.injcount += 1
+        return {"name": name, "bhp": bhp, "location": w, "delta": delta, "max_rate": max_rate, "rate": 0.0}
+
+
+class HeaterCase(_CaseBase):
+    """heatercase.py:6-118."""
+
+    def __init__(self, params, geo, well_case=None, heater_points=()):
+        self.name = "Heaters"
+        self._init_geo(params, geo)
+        self.constant_rate = False
+        heater_points = list(heater_points)
+        if well_case is not None:
+            # heatercase.py:18-51: the well presets, heaters at producers + injectors
+            table = dict(_PRESETS_2D) if geo.dim == 2 else dict(_PRESETS_3D)
+            if geo.dim == 3:
+                table["multiple"] = lambda s: (
+                    [[s.Length / 4, s.Length_y / 2, s.Length_z * 0.2], [s.Length / 2, s.Length_y / 2, s.Length_z * 0.2],
+                     [3 * s.Length / 4, s.Length_y / 2, s.Length_z * 0.2]],
+                    [[s.Length / 4, s.Length_y / 2, s.Length_z * 0.8], [s.Length / 2, s.Length_y / 2, s.Length_z * 0.8],
+                     [3 * s.Length / 4, s.Length_y / 2, s.Length_z * 0.8]])
+            if well_case in table and not (geo.dim == 2 and well_case == "default"):
+                pp, ip = table[well_case](self)
+                heater_points = pp + ip
+        self.init_heaters(heater_points, "circle")
+
+    def _radius(self):
+        return 0.1     # heatercase.py:84,98: hard-wired, not params.well_radius
+
+    def init_heaters(self, heater_points, wellfunc):
+        self.heaters = []
+        self.heatercount = 0
+        for point in heater_points:
+            self.heaters.append(self.make_heater(point, wellfunc))
+
+    def make_heater(self, w, wellfunc):
+        delta = self.well_delta(w) if wellfunc == "delta" else self.well_circle(w)
+        name = "heater" + str(self.heatercount)
+        self.heatercount += 1
+        return {"name": name, "location": w, "delta": delta}
+
+
+class WellHeaterCase(WellCase, HeaterCase):
+    """wellheatercase.py:6-12: heaters at the injector and producer points (in that order); the
+    delta functions are WellCase's (method resolution order), i.e. radius = params.well_radius."""
+
+    def __init__(self, params, geo, well_case=None, prod_points=(), inj_points=(), constant_rate=False):
+        WellCase.__init__(self, params, geo, well_case=well_case, prod_points=prod_points, inj_points=inj_points,
+                          constant_rate=constant_rate)
+        const = self.constant_rate
+        HeaterCase.__init__(self, params, geo, well_case=well_case, heater_points=list(inj_points) + list(prod_points))
+        self.constant_rate = const
+        self.name = "Wells and Heaters"
+
+    def _radius(self):
+        return getattr(self.params, "well_radius", 0.1)
+
+
+class SourceTerms(_CaseBase):
+    """sourceterms.py:6-153: one summed delta field per kind (the form for many wells,
+    thermalmodel.py:247)."""
+    _height = 0.1   # sourceterms.py:116
+
+    def __init__(self, params, geo, well_case=None, prod_points=(), inj_points=(), heater_points=(),
+                 constant_rate=False):
+        self.name = "Sources"
+        self._init_geo(params, geo)
+        if not hasattr(params, "prod_rate"):
+            params.prod_rate = params.rate      # sourceterms.py:18-25
+        if not hasattr(params, "inj_rate"):
+            params.inj_rate = params.rate
+        self.constant_rate = bool(constant_rate)
+        prod_points, inj_points = self._preset(well_case, prod_points, inj_points)
+        self.init_deltas(prod_points, inj_points, list(heater_points), "circle")
+
+    def init_deltas(self, prod_points, inj_points, heater_points, well_func):
+        deltas = self.make_deltas if well_func == "delta" else self.make_circles
+        self.deltas_prod = deltas(prod_points)
+        self.deltas_inj = deltas(inj_points)
+        self.deltas_heaters = deltas(heater_points)
+
+    def make_circles(self, ws):
+        out = np.zeros(self.geo.ncell)
+        for w in ws:
+            out += self.well_circle(w)
+        return out
+
+    def make_deltas(self, ws):
+        """sourceterms.py:126-139: coincident points do NOT accumulate here (vec[node] = 1.0)."""
+        out = np.zeros(self.geo.ncell)
+        for w in ws:
+            out[np.nonzero(self.well_delta(w))[0]] = 1.0 / self.geo.cell_volume
+        return out
+
+
+def source_entries(case, params, geo):
+    """Flatten a case into libtpb200 source records (cell, kind, weight, bhp, max_rate, const_rate)."""
+    V = geo.cell_volume
+    const = bool(getattr(case, "constant_rate", False))
+    out = []
+
+    def add(delta, kind, bhp, max_rate):
+        for c in np.nonzero(delta)[0]:
+            out.append((int(c), kind, float(delta[c] * V), float(bhp), float(max_rate), const))
+
+    if getattr(case, "name", "").startswith("Sources"):
+        add(case.deltas_prod, PROD, params.p_prod, -params.prod_rate)     # sourceterms.py:185-186
+        add(case.deltas_inj, INJ, params.p_inj, params.inj_rate)          # :159-160
+        add(case.deltas_heaters, HEATER, 0.0, 0.0)
+    for w in getattr(case, "prod_wells", []) or []:
+        add(w["delta"], PROD, w["bhp"], w["max_rate"])
+    for w in getattr(case, "inj_wells", []) or []:
+        add(w["delta"], INJ, w["bhp"], w["max_rate"])
+    for h in getattr(case, "heaters", []) or []:
+        add(h["delta"], HEATER, 0.0, 0.0)
+    return out

@@ -1,0 +1,269 @@
+"""SinglePhase / TwoPhase / ThermalModel - host-side mirror of the reference's model classes
+(singlephase.py:6-58, twophase.py:7-65, thermalmodel.py:7-412) on top of libtpb200.
+
+Same constructor signatures, the same `solver_parameters` surface (options.py) and the same time
+loop: `model.solve()` runs implicit-Euler steps, one Newton solve per step (`tpb_newton_solve`,
+standing in for `self.solver.solve()` thermalmodel.py:165), halves dt on a ConvergenceError
+(:170-180), re-solves once with dt/2 and clips when the saturation leaves [0,1] (:193-229), and
+applies the SPE10 dt heuristic (:337-345).  State lives on the GPU between steps.
+
+`run_time_loop` holds the loop logic on an abstract `newton`/`ops` pair so that it can be unit-tested
+on the CPU (tests/) without a device; the models below always bind it to the CUDA Engine.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import options as O
+from .cases import source_entries
+
+DAY = 24.0 * 3600.0
+
+
+class ConvergenceError(RuntimeError):
+    """Raised where Firedrake raises firedrake.exceptions.ConvergenceError (thermalmodel.py:170)."""
+
+    def __init__(self, reason, msg=""):
+        RuntimeError.__init__(self, "Nonlinear solve failed to converge: SNES reason %d %s" % (reason, msg))
+        self.reason = reason
+
+
+class LoopResult:
+    def __init__(self):
+        self.nits_vec, self.lits_vec, self.dt_vec, self.timings = [], [], [], []
+        self.failed_solves = 0
+        self.failed_time = 0.0
+        self.chops = 0
+        self.t = 0.0
+        self.stats = []
+
+    @property
+    def total_nits(self):
+        return int(sum(self.nits_vec))
+
+    @property
+    def total_lits(self):
+        return int(sum(self.lits_vec))
+
+
+def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_fact, two_phase, i_S, spe10,
+                  verbose=False, log=print, max_steps=None, dt0=None):
+    """thermalmodel.py:97-348.  `newton(u, u_old, dt)` solves one step in place and returns an object with
+    .nits .lits .reason (raises nothing); `ops` gives copy(dst, src), minmax(u, f) and clip(u, f, lo, hi).
+    Times are in seconds except `end`/`maxdt` (days, as in the reference)."""
+    res = LoopResult()
+    dt = maxdt * DAY                                             # thermalmodel.py:13
+    dt_init = dt_init_fact * maxdt * DAY                         # :97
+    dt_inj = maxdt * DAY                                         # :98
+    if small_dt_start:
+        dt = dt_init                                             # :101-102
+    if dt0 is not None:
+        dt = dt0
+    end_s = end * DAY
+    t = 0.0
+    i = 0
+
+    def solve_or_raise(dt_now):
+        t0 = time.perf_counter()
+        st = newton(u, u_old, dt_now)
+        el = time.perf_counter() - t0
+        if st.reason < 0:
+            res.failed_solves += 1
+            res.failed_time += el
+            raise ConvergenceError(st.reason)
+        return st, el
+
+    while t < end_s and (max_steps is None or i < max_steps):
+        i += 1
+        if verbose:
+            log("Time: %g days. Time-step %d. dt size: %g" % (t / DAY, i, dt / DAY))
+        while True:                                              # :162-181
+            try:
+                st, el = solve_or_raise(dt)
+                res.timings.append(el)
+            except ConvergenceError:
+                dt *= 0.5
+                if verbose:
+                    log("Time: %g days. Time-step %d. New dt size: %g" % (t / DAY, i, dt / DAY))
+                ops.copy(u, u_old)
+                continue
+            break
+        if two_phase:                                            # :184-229
+            eps = 1e-10
+            smin, smax = ops.minmax(u, i_S)
+            chop = (smax - 1.0 > eps) or (smin < -eps)
+            while chop:
+                if verbose:
+                    log("------Negative saturation! Chopping time-step---------")
+                res.chops += 1
+                dt *= 0.5
+                ops.copy(u, u_old)
+                try:
+                    st, el = solve_or_raise(dt)
+                except ConvergenceError:
+                    dt *= 0.5
+                    ops.copy(u, u_old)
+                    continue
+                break                                            # :218 (the re-check below it is dead code)
+            ops.clip(u, i_S, 0.0, 1.0)                           # :226-229
+        ops.copy(u_old, u)                                       # :296
+        t += dt
+        res.dt_vec.append(dt)
+        res.nits_vec.append(st.nits)                             # :327-336
+        res.lits_vec.append(st.lits)
+        res.stats.append(st)
+        if verbose:
+            log("Nonlinear iterations: %d\nLinear iterations: %d" % (st.nits, st.lits))
+        current_dt = dt
+        if spe10:                                                # :337-345
+            if st.nits < 6:
+                factor = 1 + min(1.0, (6 - st.nits) ** 2 / 3 ** 2)
+                dt = min(dt_inj, current_dt * factor)
+            elif st.nits > 9:
+                factor = 1 - min(1.0, (st.nits - 9) ** 2 / 4 ** 2) / 2
+                dt = current_dt * factor
+        if dt > end_s - t and t < end_s:                         # :346-348
+            dt = end_s - t
+    res.t = t
+    res.next_dt = dt
+    return res
+
+
+class _TorchOps:
+    def __init__(self, engine):
+        self.e = engine
+
+    def copy(self, dst, src):
+        dst.copy_(src)
+
+    def minmax(self, u, f):
+        return self.e.field_minmax(u, f)
+
+    def clip(self, u, f, lo, hi):
+        self.e.clip_field(u, f, lo, hi)
+
+
+class ThermalModel:
+    """thermalmodel.py:7-412 with the Firedrake solver replaced by a libtpb200 handle."""
+    nphase = 1
+
+    def __init__(self, end=1.0, maxdt=0.005, save=False, n_save=2, small_dt_start=True, checkpointing=None,
+                 filename="results/results.txt", dt_init_fact=2 ** (-10), verbosity=True, device=0):
+        from .engine import Engine
+        from . import _lib as L
+        if save:
+            raise NotImplementedError("pvd/VTK output is outside the hot path (SURVEY.md 8f)")
+        if checkpointing and (checkpointing.get("save") or checkpointing.get("load")):
+            raise NotImplementedError("HDF5 checkpoints are outside the hot path (SURVEY.md 8f)")
+        self.maxdt, self.dt_init_fact, self.end, self.verbosity = maxdt, dt_init_fact, end, verbosity
+        self.filename = filename
+        geo, prm = self.geo, self.params
+        self.engine = Engine(geo.dim, geo.Nx, geo.Ny, getattr(geo, "Nz", 1), geo.Dx, geo.Dy,
+                             getattr(geo, "Dz", 1.0), self.nphase, prm, device=device)
+        e = self.engine
+        e.set_field(L.TPB_PHI, geo.phi)
+        e.set_field(L.TPB_KX, geo.K_x)
+        e.set_field(L.TPB_KY, geo.K_y)
+        if geo.dim == 3:
+            e.set_field(L.TPB_KZ, geo.K_z)
+        if self.nphase == 1:
+            e.set_field(L.TPB_KT, geo.kT)
+        e.set_sources(source_entries(self.case, prm, geo))
+        e.set_solver_opts(**self.solver_opts)
+        self.initial_condition = self.init_IC_uniform()
+        self.u = e.tensor(self.initial_condition)
+        self.u_ = self.u.clone()
+        self.total_nits = self.total_lits = 0
+        self.last_dt = None
+        self.result = None
+
+    def resultprint(self, *args):
+        if self.verbosity:
+            print(*args)
+
+    def solve(self, max_steps=None):
+        e = self.engine
+        self.u.copy_(e.tensor(self.initial_condition))
+        self.u_.copy_(self.u)
+        res = run_time_loop(lambda u, uo, dt: e.newton_solve(u, uo, dt), _TorchOps(e), self.u, self.u_,
+                            end=self.end, maxdt=self.maxdt, small_dt_start=self.small_dt_start,
+                            dt_init_fact=self.dt_init_fact, two_phase=self.nphase == 2, i_S=2,
+                            spe10=self.geo.name.startswith("SPE10"), verbose=self.verbosity, max_steps=max_steps)
+        self.result = res
+        self.total_nits, self.total_lits = res.total_nits, res.total_lits
+        self.last_dt = res.dt_vec[-1] if res.dt_vec else None
+        if self.verbosity and res.dt_vec:                       # thermalmodel.py:367-408
+            p = self.resultprint
+            p("nits = ", res.nits_vec, ";")
+            p("lits = ", res.lits_vec, ";")
+            p("dts = ", res.dt_vec, ";")
+            p("timings = ", res.timings, ";")
+            p(self.name, "thermal model")
+            p("Geo model: ", self.geo.name)
+            p("Test case: ", self.case.name)
+            p("Solver: ", self.solver_desc)
+            p("Total CPU time (s):", sum(res.timings))
+            n = len(res.dt_vec)
+            p("Average Nonlinear iterations per time-step:", res.total_nits / n)
+            p("Average Linear iterations per time-step: ", res.total_lits / n)
+            p("Average Linear iteration per Nonlinear iteration: ", res.total_lits / max(res.total_nits, 1))
+            p("Number of time-steps: ", n)
+        return res
+
+    def fields(self):
+        """converged fields as host arrays: (p, T[, S_o])."""
+        return tuple(self.u.detach().cpu().numpy())
+
+
+class SinglePhase(ThermalModel):
+    """singlephase.py:6-58."""
+    nphase = 1
+
+    def __init__(self, geo, case, params, end=1.0, maxdt=0.005, save=False, n_save=2, small_dt_start=True,
+                 checkpointing=None, solver_parameters=None, filename="results/results.txt",
+                 dt_init_fact=2 ** (-10), vector=False, gravity2D=False, verbosity=True, device=0):
+        self.name = "Single phase"
+        self.geo, self.case, self.params = geo, case, params
+        if vector:
+            raise NotImplementedError("vector=True (interleaved p,T layout) is not realised; see SURVEY.md 8f rank 3")
+        if gravity2D:
+            raise NotImplementedError("gravity2D is orientation-ill-defined on a non-extruded mesh (SURVEY.md appendix 5)")
+        self.vector = False
+        self.small_dt_start = small_dt_start
+        self.solver_parameters = solver_parameters
+        self.solver_opts, self.decoup, self.solver_desc = O.resolve(solver_parameters, 1)
+        ThermalModel.__init__(self, end, maxdt, save, n_save, small_dt_start, checkpointing, filename,
+                              dt_init_fact, verbosity, device)
+
+    def init_IC_uniform(self):
+        n = self.geo.ncell
+        return np.stack([np.full(n, self.params.p_ref), np.full(n, self.params.T_prod)])
+
+
+class TwoPhase(ThermalModel):
+    """twophase.py:7-65."""
+    nphase = 2
+
+    def __init__(self, geo, case, params, end=1.0, maxdt=0.005, save=False, n_save=2, small_dt_start=True,
+                 checkpointing=None, solver_parameters=None, filename="results/results.txt",
+                 dt_init_fact=2 ** (-10), vector=False, gravity2D=False, verbosity=True, device=0):
+        self.name = "Two-phase"
+        self.geo, self.case, self.params = geo, case, params
+        if vector:
+            raise NotImplementedError("vector=True (interleaved p,T layout) is not realised; see SURVEY.md 8f rank 3")
+        if gravity2D:
+            raise NotImplementedError("gravity2D is orientation-ill-defined on a non-extruded mesh (SURVEY.md appendix 5)")
+        self.vector = False
+        self.i_S_o = 2
+        self.small_dt_start = small_dt_start
+        self.solver_parameters = solver_parameters
+        self.solver_opts, self.decoup, self.solver_desc = O.resolve(solver_parameters, 2)
+        ThermalModel.__init__(self, end, maxdt, save, n_save, small_dt_start, checkpointing, filename,
+                              dt_init_fact, verbosity, device)
+
+    def init_IC_uniform(self):
+        n = self.geo.ncell
+        p = self.params
+        return np.stack([np.full(n, p.p_ref), np.full(n, p.T_prod), np.full(n, p.S_o)])
