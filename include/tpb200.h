@@ -121,7 +121,7 @@ typedef struct {
     int reason;               /* SNESConvergedReason numbering: >0 converged, <0 diverged */
     int nfev;                 /* residual evaluations (line search included) */
     double fnorm0, fnorm;
-    double t_assemble_ms, t_pcsetup_ms, t_ksp_ms, t_total_ms;  /* CUDA-event timings */
+    double t_assemble_ms, t_pcsetup_ms, t_ksp_ms, t_total_ms;  /* host clock around stream-synchronised phases */
 } tpb_stats;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
@@ -179,6 +179,15 @@ int tpb_dot(tpb_handle h, const double* x, const double* y, size_t n, double* ou
 int tpb_comm_init(tpb_handle h, const void* nccl_unique_id, int rank, int nranks);
 int tpb_comm_unique_id(void* out128);
 int tpb_exchange_static(tpb_handle h);   /* ghost planes of phi,K*,kT after tpb_set_field */
+
+/* ---- preconditioner introspection (component-level parity tests; also handy when porting) ---- */
+/* which: 0 = pressure hierarchy, 1 = temperature (Schur) hierarchy */
+int tpb_pc_mg_nlevels(tpb_handle h, int which);
+/* dims6 = nx,ny,nz of level l and its coarsening factors cx,cy,cz; op_out (device, ns*n_l doubles, may be NULL) */
+int tpb_pc_mg_level(tpb_handle h, int which, int l, int* dims6, double* op_out);
+int tpb_pc_mg_apply(tpb_handle h, int which, const double* b, double* y);      /* y = V-cycle(b), device */
+int tpb_pc_stage2_apply(tpb_handle h, const double* r, double* z);              /* z = ILU(0)^-1 r, device */
+int tpb_pc_get_weights(tpb_handle h, int f, double* out);                      /* decoupling weights w_f, device */
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */

@@ -1214,6 +1214,7 @@ static void ksp_solve(tpc_handle_s* h, const double* J, const double* b, double*
             gv[k] = cs[k] * gv[k];
             rnorm = fabs(gv[k + 1]);
             its++;
+            if (o->verbose >= 2) fprintf(stderr, "    [cpu] ksp %3d  %.6e  (h %.3e)\n", its, rnorm, hn);
             if (!(rnorm == rnorm)) reason = -9;
             else if (rnorm <= tol) reason = 2;
             else if (its >= o->ksp_max_it) reason = -3;

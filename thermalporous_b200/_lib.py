@@ -59,7 +59,8 @@ SYMBOLS = [
     "tpb_solver_defaults", "tpb_set_solver_opts", "tpb_pc_setup", "tpb_pc_apply", "tpb_ksp_solve",
     "tpb_newton_solve", "tpb_newton_solve_host", "tpb_field_minmax", "tpb_clip_field", "tpb_dot",
     "tpb_comm_init", "tpb_comm_unique_id", "tpb_exchange_static", "tpb_launch_count", "tpb_time_kernel",
-    "tpb_stream", "tpb_sync",
+    "tpb_stream", "tpb_sync", "tpb_pc_mg_nlevels", "tpb_pc_mg_level", "tpb_pc_mg_apply", "tpb_pc_stage2_apply",
+    "tpb_pc_get_weights",
 ]
 
 _lib = None
@@ -113,6 +114,11 @@ def load():
     lib.tpb_stream.argtypes = [vp]
     lib.tpb_stream.restype = vp
     lib.tpb_sync.argtypes = [vp]
+    lib.tpb_pc_mg_nlevels.argtypes = [vp, i]
+    lib.tpb_pc_mg_level.argtypes = [vp, i, i, C.POINTER(i * 6), dp]
+    lib.tpb_pc_mg_apply.argtypes = [vp, i, dp, dp]
+    lib.tpb_pc_stage2_apply.argtypes = [vp, dp, dp]
+    lib.tpb_pc_get_weights.argtypes = [vp, i, dp]
     _lib = lib
     return lib
 

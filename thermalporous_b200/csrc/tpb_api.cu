@@ -12,6 +12,11 @@ void tpb_clip_impl(tpb_handle_s* h, size_t n, double* x, double lo, double hi);
 void tpb_comm_init_impl(tpb_handle_s* h, const void* id128, int rank, int nranks);
 void tpb_comm_unique_id_impl(void* out128);
 void tpb_allreduce_max(tpb_handle_s* h, double* dev_buf, int count);
+int tpb_pc_mg_nlevels_impl(tpb_handle_s* h, int which);
+int tpb_pc_mg_level_impl(tpb_handle_s* h, int which, int l, int* dims6, double* op_out);
+void tpb_pc_mg_apply_impl(tpb_handle_s* h, int which, const double* b, double* y);
+void tpb_pc_stage2_apply_impl(tpb_handle_s* h, const double* r, double* z);
+const double* tpb_pc_weights_impl(tpb_handle_s* h, int f);
 
 static thread_local std::string g_err;
 
@@ -409,6 +414,37 @@ int tpb_exchange_static(tpb_handle h) {
     TPB_REQUIRE(h, TPB_ERR_ARG, "null handle");
     for (int f = 0; f < 5; f++)
         if (h->fld_set[f]) tpb_halo_vector(h, h->fld[f], 1, h->fld_lo[f], h->fld_hi[f]);
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    TPB_CATCH(h)
+}
+
+int tpb_pc_mg_nlevels(tpb_handle h, int which) { return h ? tpb_pc_mg_nlevels_impl(h, which) : 0; }
+int tpb_pc_mg_level(tpb_handle h, int which, int l, int* dims6, double* op_out) {
+    TPB_TRY(h)
+    TPB_REQUIRE(h, TPB_ERR_ARG, "null handle");
+    TPB_REQUIRE(tpb_pc_mg_level_impl(h, which, l, dims6, op_out) == 0, TPB_ERR_ARG, "no such multigrid level");
+    TPB_CATCH(h)
+}
+int tpb_pc_mg_apply(tpb_handle h, int which, const double* b, double* y) {
+    TPB_TRY(h)
+    TPB_REQUIRE(h && b && y, TPB_ERR_ARG, "null argument");
+    tpb_pc_mg_apply_impl(h, which, b, y);
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    TPB_CATCH(h)
+}
+int tpb_pc_stage2_apply(tpb_handle h, const double* r, double* z) {
+    TPB_TRY(h)
+    TPB_REQUIRE(h && r && z, TPB_ERR_ARG, "null argument");
+    tpb_pc_stage2_apply_impl(h, r, z);
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    TPB_CATCH(h)
+}
+int tpb_pc_get_weights(tpb_handle h, int f, double* out) {
+    TPB_TRY(h)
+    TPB_REQUIRE(h && out && f >= 0 && f < h->nf, TPB_ERR_ARG, "bad argument");
+    const double* w = tpb_pc_weights_impl(h, f);
+    TPB_REQUIRE(w != nullptr, TPB_ERR_STATE, "no decoupling weights (stage 1 not set up)");
+    TPB_CUDA(cudaMemcpyAsync(out, w, h->g.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     TPB_CUDA(cudaStreamSynchronize(h->stream));
     TPB_CATCH(h)
 }

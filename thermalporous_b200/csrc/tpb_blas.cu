@@ -71,13 +71,13 @@ struct Coef {
 
 template <int K>
 __global__ void __launch_bounds__(256) maxpy_kernel(size_t n, double* __restrict__ y, const double* __restrict__ V,
-                                                    size_t ldv, int kact, Coef cf) {
+                                                    size_t ldv, int kact, Coef cf, double scale) {
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
         double a = y[i];
 #pragma unroll
         for (int j = 0; j < K; j++)
-            if (j < kact) a = fma(cf.c[j], V[(size_t)j * ldv + i], a);
-        y[i] = a;
+            if (j < kact) a = fma(-cf.c[j], V[(size_t)j * ldv + i], a);
+        y[i] = a * scale;
     }
 }
 
@@ -180,20 +180,31 @@ void tpb_copy(tpb_handle_s* h, size_t n, const double* x, double* y) {
 }
 void tpb_zero(tpb_handle_s* h, size_t n, double* x) { TPB_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), h->stream)); }
 
-void tpb_mdot(tpb_handle_s* h, size_t n, const double* x, const double* Y, size_t ldy, int k, double* host_out) {
+// k dots <x, Y_j> queued on the stream; results land in h->red_out[out_off + j] (device)
+void tpb_mdot_dev(tpb_handle_s* h, size_t n, const double* x, const double* Y, size_t ldy, int k, int out_off) {
     ensure_red(h);
-    TPB_REQUIRE(k <= h->red_cap, TPB_ERR_ARG, "mdot: too many vectors");
+    TPB_REQUIRE(out_off + k <= h->red_cap, TPB_ERR_ARG, "mdot: too many vectors");
     unsigned blocks = grid_for(n, RB);
     for (int j0 = 0; j0 < k; j0 += KC) {
         int kact = k - j0 < KC ? k - j0 : KC;
         mdot_kernel<KC><<<blocks, RB, 0, h->stream>>>(n, x, Y + (size_t)j0 * ldy, ldy, kact, h->red_partial,
-                                                      h->red_counter, h->red_out + j0);
+                                                      h->red_counter, h->red_out + out_off + j0);
         h->launches++;
     }
-    tpb_allreduce_sum(h, h->red_out, k);
-    TPB_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, k * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+}
+
+// sum the first `count` queued results over the ranks, copy them to the host and synchronise
+void tpb_red_get(tpb_handle_s* h, int count, double* host_out) {
+    ensure_red(h);
+    tpb_allreduce_sum(h, h->red_out, count);
+    TPB_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     TPB_CUDA(cudaStreamSynchronize(h->stream));
-    for (int j = 0; j < k; j++) host_out[j] = h->red_host[j];
+    for (int j = 0; j < count; j++) host_out[j] = h->red_host[j];
+}
+
+void tpb_mdot(tpb_handle_s* h, size_t n, const double* x, const double* Y, size_t ldy, int k, double* host_out) {
+    tpb_mdot_dev(h, n, x, Y, ldy, k, 0);
+    tpb_red_get(h, k, host_out);
 }
 
 double tpb_dot_sync(tpb_handle_s* h, size_t n, const double* x, const double* y) {
@@ -208,9 +219,19 @@ void tpb_maxpy(tpb_handle_s* h, size_t n, double* y, const double* V, size_t ldv
         int kact = k - j0 < KC ? k - j0 : KC;
         Coef cf;
         for (int j = 0; j < KC; j++) cf.c[j] = j < kact ? c[j0 + j] : 0.0;
-        maxpy_kernel<KC><<<grid_for(n, 256), 256, 0, h->stream>>>(n, y, V + (size_t)j0 * ldv, ldv, kact, cf);
+        maxpy_kernel<KC><<<grid_for(n, 256), 256, 0, h->stream>>>(n, y, V + (size_t)j0 * ldv, ldv, kact, cf, 1.0);
         h->launches++;
     }
+}
+
+// y = scale * (y - sum_j c[j] V_j) for one group of <= KC contiguous vectors
+void tpb_maxpy_scale(tpb_handle_s* h, size_t n, double* y, const double* V, size_t ldv, int k, const double* c,
+                     double scale) {
+    TPB_REQUIRE(k <= KC, TPB_ERR_ARG, "maxpy_scale: group too large");
+    Coef cf;
+    for (int j = 0; j < KC; j++) cf.c[j] = j < k ? c[j] : 0.0;
+    maxpy_kernel<KC><<<grid_for(n, 256), 256, 0, h->stream>>>(n, y, V, ldv, k, cf, scale);
+    h->launches++;
 }
 
 void tpb_minmax_impl(tpb_handle_s* h, size_t n, const double* x, double* out2) {

@@ -294,6 +294,10 @@ void tpb_copy(tpb_handle_s* h, size_t n, const double* x, double* y);
 void tpb_zero(tpb_handle_s* h, size_t n, double* x);
 // k dots <x, Y_j> (Y_j = Y + j*ldy), results in h->red_host[0..k) after sync (global over ranks)
 void tpb_mdot(tpb_handle_s* h, size_t n, const double* x, const double* Y, size_t ldy, int k, double* host_out);
+void tpb_mdot_dev(tpb_handle_s* h, size_t n, const double* x, const double* Y, size_t ldy, int k, int out_off);
+void tpb_red_get(tpb_handle_s* h, int count, double* host_out);
+void tpb_maxpy_scale(tpb_handle_s* h, size_t n, double* y, const double* V, size_t ldv, int k, const double* c,
+                     double scale);
 double tpb_norm2(tpb_handle_s* h, size_t n, const double* x);
 double tpb_dot_sync(tpb_handle_s* h, size_t n, const double* x, const double* y);
 // y -= sum_j c[j] V_j  (c on host)

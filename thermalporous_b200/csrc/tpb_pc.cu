@@ -1,0 +1,1141 @@
+// tpb_pc.cu - K3-K8: the two-stage preconditioner.
+//
+// Stage 1 (reference: CPRStage1PC preconditioners.py:335-906, CPTRStage1PC :1243-1571, PCFIELDSPLIT
+// schur FULL singlephase.py:309-319 / twophase.py:536-545, ConvDiffSchur(TwoPhases)PC :11-333):
+//   K3  block extraction straight from the block-stencil Jacobian (no re-assembly)
+//   K5  QI / TI / QI_temp / TI_temp decoupling   Atilde_pp = A_pp - D_ps D_ss^-1 A_sp
+//   K6  restriction r_p = x_p - D_ps D_ss^-1 x_s, prolongation y = [y_p; 0]
+//   K4  ConvDiff temperature operator with coefficients frozen at the Newton state
+//   K7  scalar-stencil multigrid V-cycle in the role of hypre BoomerAMG (one V-cycle per apply):
+//       piecewise-constant aggregation with per-level semi-coarsening (an axis is coarsened only
+//       where its mean coupling is strong), Galerkin coarse operators (stay 5|7-point), red-black
+//       Gauss-Seidel smoothing; the coarsest levels (<= TAIL_CELLS cells) run inside one CTA.
+// Stage 2 (reference: PETSc bjacobi + ilu(0), singlephase.py:348-349, twophase.py:547-548):
+//   K8  block ILU(0) of the nf x nf block stencil in red-black ordering: for a 5|7-point stencil
+//       ILU(0) only modifies the diagonal blocks, D_b = A_bb - sum_r A_br A_rr^-1 A_rb, and both
+//       triangular solves are two fully parallel colour sweeps.
+// PCCOMPOSITE multiplicative: y = B1 x ; y += B2 (x - J y).
+#include <math.h>
+
+#include <algorithm>
+
+#include "tpb_internal.cuh"
+
+namespace {
+
+constexpr int MAXLEV = 40;
+
+struct MgLevel {
+    int nx = 0, ny = 0, nz = 0;
+    long long n = 0;
+    int cx = 1, cy = 1, cz = 1;
+    double* a = nullptr;  // ns * n
+    bool own_a = false;
+    double* x = nullptr;
+    double* b = nullptr;
+};
+
+struct MgHier {
+    int nlev = 0;
+    MgLevel lev[MAXLEV];
+};
+
+}  // namespace
+
+struct PcState {
+    const double* J = nullptr;
+    double* w[TPB_MAXF] = {nullptr, nullptr, nullptr};
+    double* App = nullptr;
+    double* A00 = nullptr;
+    double* AT = nullptr;
+    MgHier mg_p, mg_T;
+    double* Dinv = nullptr;
+    double *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
+    double* strength = nullptr;  // 3 doubles (device)
+    bool ready = false;
+};
+
+namespace {
+
+__host__ __device__ __forceinline__ int opp_slot(int s) { return s == 0 ? 0 : (((s - 1) ^ 1) + 1); }
+
+// neighbour of cell (i,j,k) through stencil slot s on an (nx,ny,nz) box; -1 when outside
+__device__ __forceinline__ long long nbr_cell(int nx, int ny, int nz, int i, int j, int k, long long c, int s) {
+    switch (s) {
+        case 0: return c;
+        case 1: return i > 0 ? c - 1 : -1;
+        case 2: return i < nx - 1 ? c + 1 : -1;
+        case 3: return j > 0 ? c - nx : -1;
+        case 4: return j < ny - 1 ? c + nx : -1;
+        case 5: return k > 0 ? c - (long long)nx * ny : -1;
+        default: return k < nz - 1 ? c + (long long)nx * ny : -1;
+    }
+}
+
+__device__ __forceinline__ void inv_block(int m, const double* A, double* Ai) {
+    if (m == 1) {
+        Ai[0] = 1.0 / A[0];
+    } else if (m == 2) {
+        double det = A[0] * A[3] - A[1] * A[2], id = 1.0 / det;
+        Ai[0] = A[3] * id;
+        Ai[1] = -A[1] * id;
+        Ai[2] = -A[2] * id;
+        Ai[3] = A[0] * id;
+    } else {
+        double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+        double det = A[0] * c00 + A[1] * c01 + A[2] * c02, id = 1.0 / det;
+        Ai[0] = c00 * id;
+        Ai[1] = (A[2] * A[7] - A[1] * A[8]) * id;
+        Ai[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+        Ai[3] = c01 * id;
+        Ai[4] = (A[0] * A[8] - A[2] * A[6]) * id;
+        Ai[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+        Ai[6] = c02 * id;
+        Ai[7] = (A[1] * A[6] - A[0] * A[7]) * id;
+        Ai[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+    }
+}
+
+#define JAT(s, r, q, c) J[((long long)((s) * NF + (r)) * NF + (q)) * n + (c)]
+
+// column sum of block (r,q) over every row that points at column cell c (TI decoupling:
+// transpose + getRowSum, preconditioners.py:693-703)
+template <int NF, int DIM>
+__device__ __forceinline__ double colsum(const double* __restrict__ J, long long n, int nx, int ny, int nz, int i,
+                                         int j, int k, long long c, int r, int q) {
+    double sum = JAT(0, r, q, c);
+#pragma unroll
+    for (int s = 1; s < 2 * DIM + 1; s++) {
+        long long nb = nbr_cell(nx, ny, nz, i, j, k, c, s);
+        if (nb >= 0) sum += JAT(opp_slot(s), r, q, nb);
+    }
+    return sum;
+}
+
+// ---- K3 + K5 for CPR: weights w[f] and the decoupled pressure stencil ------------------------
+template <int NF, int DIM>
+__global__ void __launch_bounds__(128) cpr_setup_kernel(const double* __restrict__ J, Geom g, int dec, double* w1,
+                                                        double* w2, double* __restrict__ App) {
+    const long long n = g.n;
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    int i = (int)(c % nx);
+    long long t = c / nx;
+    int j = (int)(t % ny), k = (int)(t / ny);
+    constexpr int L = NF - 1;
+    double wf[TPB_MAXF] = {0.0, 0.0, 0.0};
+    if (dec == TPB_DECOUP_QI) {
+        wf[L] = JAT(0, 0, L, c) / JAT(0, L, L, c);
+    } else if (dec == TPB_DECOUP_TI) {
+        wf[L] = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, 0, L) / colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, L, L);
+    } else if (NF == 3 && (dec == TPB_DECOUP_QI_TEMP || dec == TPB_DECOUP_TI_TEMP)) {
+        double B[4], Bi[4], pT, pS;
+        if (dec == TPB_DECOUP_TI_TEMP) {
+            B[0] = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, 1, 1);
+            B[1] = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, 1, NF - 1);
+            B[2] = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, NF - 1, 1);
+            B[3] = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, NF - 1, NF - 1);
+            pT = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, 0, 1);
+            pS = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, 0, NF - 1);
+        } else {
+            B[0] = JAT(0, 1, 1, c);
+            B[1] = JAT(0, 1, NF - 1, c);
+            B[2] = JAT(0, NF - 1, 1, c);
+            B[3] = JAT(0, NF - 1, NF - 1, c);
+            pT = JAT(0, 0, 1, c);
+            pS = JAT(0, 0, NF - 1, c);
+        }
+        inv_block(2, B, Bi);
+        wf[1] = pT * Bi[0] + pS * Bi[2];
+        wf[NF - 1] = pT * Bi[1] + pS * Bi[3];
+    }
+    w1[c] = wf[1];
+    if (NF == 3) w2[c] = wf[2];
+#pragma unroll
+    for (int s = 0; s < 2 * DIM + 1; s++) {
+        double v = JAT(s, 0, 0, c);
+#pragma unroll
+        for (int f = 1; f < NF; f++) v -= wf[f] * JAT(s, f, 0, c);
+        App[(long long)s * n + c] = v;
+    }
+}
+
+// ---- K3 + K5 for CPTR / single-phase field-split: 2x2 primary block --------------------------
+template <int NF, int DIM>
+__global__ void __launch_bounds__(128) cptr_setup_kernel(const double* __restrict__ J, Geom g, int dec, int a11,
+                                                         double* w0, double* w1, double* __restrict__ A00,
+                                                         double* __restrict__ App, double* __restrict__ AT) {
+    const long long n = g.n;
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    int i = (int)(c % nx);
+    long long t = c / nx;
+    int j = (int)(t % ny), k = (int)(t / ny);
+    double wa[2] = {0.0, 0.0};
+    if (NF == 3 && dec == TPB_DECOUP_QI) {
+        double dss = JAT(0, NF - 1, NF - 1, c);
+        wa[0] = JAT(0, 0, NF - 1, c) / dss;
+        wa[1] = JAT(0, 1, NF - 1, c) / dss;
+    } else if (NF == 3 && dec == TPB_DECOUP_TI) {
+        double dss = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, NF - 1, NF - 1);
+        wa[0] = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, 0, NF - 1) / dss;
+        wa[1] = colsum<NF, DIM>(J, n, nx, ny, nz, i, j, k, c, 1, NF - 1) / dss;
+    }
+    w0[c] = wa[0];
+    w1[c] = wa[1];
+#pragma unroll
+    for (int s = 0; s < 2 * DIM + 1; s++)
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                double v = JAT(s, a, b, c);
+                if (NF == 3) v -= wa[a] * JAT(s, NF - 1, b, c);
+                A00[((long long)(s * 2 + a) * 2 + b) * n + c] = v;
+                if (a == 0 && b == 0) App[(long long)s * n + c] = v;
+                if (a == 1 && b == 1 && a11) AT[(long long)s * n + c] = v;
+            }
+}
+
+// ---- K4: ConvDiff temperature operator (preconditioners.py:63-108, 225-276) ------------------
+struct CdCell {
+    double p, T, ro, rw, lo, lw, kT;
+};
+template <int NF>
+__device__ __forceinline__ CdCell cd_props(const DevParams& P, const double* __restrict__ u, long long n, long long c,
+                                           double phi, double kTs) {
+    CdCell q;
+    q.p = u[c];
+    q.T = u[n + c];
+    double a, b, imo, imo_T;
+    oil_rho_d(P, q.p, q.T, q.ro, a, b);
+    oil_imu_d(P, q.T, imo, imo_T);
+    if (NF == 3) {
+        double S = u[2 * n + c], imw, imw_T;
+        water_rho_d(q.p, q.T, q.rw, a, b);
+        water_imu_d(q.T, imw, imw_T);
+        q.lo = S * q.ro * imo;
+        q.lw = (1.0 - S) * q.rw * imw;
+        q.kT = phi * (S * P.ko + (1.0 - S) * P.kw) + (1.0 - phi) * P.kr;
+    } else {
+        q.rw = 0.0;
+        q.lw = 0.0;
+        q.lo = q.ro * imo;
+        q.kT = kTs;
+    }
+    return q;
+}
+__device__ __forceinline__ double harm_d(double a, double b) {
+    double s = 0.5 * (a + b);
+    return s > 0.0 ? a * b / s : 0.0;
+}
+
+template <int NF, int DIM>
+__global__ void __launch_bounds__(128) convdiff_kernel(const double* __restrict__ u, const double* __restrict__ phi_f,
+                                                       const double* __restrict__ Kx, const double* __restrict__ Ky,
+                                                       const double* __restrict__ Kz, const double* __restrict__ kT_f,
+                                                       double idt, Geom g, DevParams P, double* __restrict__ A) {
+    const long long n = g.n;
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    int i = (int)(c % nx);
+    long long t = c / nx;
+    int j = (int)(t % ny), k = (int)(t / ny);
+    double phi = phi_f[c];
+    CdCell me = cd_props<NF>(P, u, n, c, phi, NF == 2 ? kT_f[c] : 0.0);
+    double diag;
+    if (NF == 2)
+        diag = g.vol * idt * (phi * P.c_v_o * me.ro + (1.0 - phi) * P.rho_r * P.c_r);
+    else {
+        double S = u[2 * n + c];
+        diag = g.vol * idt * (phi * P.c_v_o * S * me.ro + phi * P.c_v_w * (1.0 - S) * me.rw + (1.0 - phi) * P.rho_r * P.c_r);
+    }
+#pragma unroll
+    for (int s = 1; s < 2 * DIM + 1; s++) {
+        long long nb = nbr_cell(nx, ny, nz, i, j, k, c, s);
+        double off = 0.0;
+        if (nb >= 0) {
+            const int axis = (s - 1) >> 1;
+            const bool hi = ((s - 1) & 1) != 0;
+            const double* Kax = axis == 0 ? Kx : (axis == 1 ? Ky : Kz);
+            CdCell ot = cd_props<NF>(P, u, n, nb, phi_f[nb], NF == 2 ? kT_f[nb] : 0.0);
+            const CdCell& pl = hi ? me : ot;
+            const CdCell& mi = hi ? ot : me;
+            double Kf = harm_d(Kax[c], Kax[nb]);
+            double grav = axis == 2 ? P.g : 0.0;
+            double ih = 1.0 / g.h[axis], area = g.area[axis];
+            double dp = ih * (pl.p - mi.p);
+            double sgn = hi ? 1.0 : -1.0;
+            double flo = dp - 0.5 * grav * (pl.ro + mi.ro);
+            bool upo = flo > 0.0;
+            double co = area * Kf * P.c_v_o * (upo ? pl.lo : mi.lo) * flo;
+            if (hi ? upo : !upo) diag += sgn * co; else off += sgn * co;
+            if (NF == 3) {
+                double flw = dp - 0.5 * grav * (pl.rw + mi.rw);
+                bool upw = flw > 0.0;
+                double cw = area * Kf * P.c_v_w * (upw ? pl.lw : mi.lw) * flw;
+                if (hi ? upw : !upw) diag += sgn * cw; else off += sgn * cw;
+            }
+            double d = area * harm_d(pl.kT, mi.kT) * ih;
+            diag += d;
+            off -= d;
+        }
+        A[(long long)s * n + c] = off;
+    }
+    A[c] = diag;
+}
+
+// producers and heaters add to the diagonal of the ConvDiff operator (preconditioners.py:91-108, 257-276);
+// the coefficient of T in the producers' energy sink is -w (sum rho q c_v) = (energy source term)/T
+__device__ __forceinline__ double peaceman_wi_d(double Kx, double Ky) {
+    const double hh = 5.0, rw = 0.1, Dx = 5.0, Dy = 5.0;
+    double a = Ky / Kx, b = Kx / Ky;
+    double ro = 0.28 * sqrt(sqrt(a) * Dx * Dx + sqrt(b) * Dy * Dy) / (sqrt(sqrt(a)) + sqrt(sqrt(b)));
+    return 2.0 * 3.141592653589793 * hh * sqrt(Kx * Ky) / log(ro / rw);
+}
+__device__ __forceinline__ double rate_value(const tpb_source& s, double wi, double imu, double p) {
+    if (s.const_rate) return s.max_rate;
+    double d = s.bhp - p;
+    double dd = s.max_rate < 0.0 ? (d >= 0.0 ? 0.0 : d) : (d <= 0.0 ? 0.0 : d);
+    double rate = wi * imu * dd;
+    return (fabs(rate) - fabs(s.max_rate) >= 0.0) ? s.max_rate : rate;
+}
+template <int NF>
+__global__ void convdiff_sources_kernel(int ncells, const int64_t* __restrict__ cells, const int* __restrict__ off,
+                                        const tpb_source* __restrict__ ent, const double* __restrict__ u,
+                                        const double* __restrict__ Kx, const double* __restrict__ Ky, long long n,
+                                        DevParams P, double* __restrict__ A) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncells) return;
+    long long c = cells[t];
+    double p = u[c], T = u[n + c];
+    double add = 0.0;
+    for (int e = off[t]; e < off[t + 1]; e++) {
+        tpb_source s = ent[e];
+        if (s.kind == TPB_HEATER) {
+            add += s.weight * P.U;
+        } else if (s.kind == TPB_PROD) {
+            double wi = s.const_rate ? 0.0 : peaceman_wi_d(Kx[c], Ky[c]);
+            double ro, a, b, imo, imo_T;
+            oil_rho_d(P, p, T, ro, a, b);
+            oil_imu_d(P, T, imo, imo_T);
+            if (NF == 2) {
+                double q = rate_value(s, wi, imo, p);
+                add -= s.weight * ro * q * P.c_v_o;
+            } else {
+                double S = u[2 * n + c], rw, imw, imw_T;
+                water_rho_d(p, T, rw, a, b);
+                water_imu_d(T, imw, imw_T);
+                double mob_o = S * imo, mob_w = (1.0 - S) * imw, imu = mob_o + mob_w;
+                double q = rate_value(s, wi, imu, p);
+                double mu = 1.0 / imu;
+                double qw = mob_w * mu * q, qo = mob_o * mu * q;
+                add -= s.weight * (rw * qw * P.c_v_w + ro * qo * P.c_v_o);
+            }
+        }
+    }
+    A[c] += add;
+}
+
+// ---- K7 multigrid kernels ---------------------------------------------------------------------
+struct LevGeom {
+    int nx, ny, nz, cx, cy, cz;
+    long long n;
+};
+
+// sum over cells of |a[2ax+1]| + |a[2ax+2]| for the three axes -> out[0..2] (atomics; a few thousand adds)
+template <int NS>
+__global__ void __launch_bounds__(256) strength_kernel(const double* __restrict__ a, long long n, double* out) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int ax = 0; ax < (NS - 1) / 2; ax++)
+            acc[ax] += fabs(a[(long long)(2 * ax + 1) * n + c]) + fabs(a[(long long)(2 * ax + 2) * n + c]);
+    }
+    __shared__ double sm[3][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        double v = acc[ax];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sm[ax][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int w = 0; w < 8; w++) v += sm[threadIdx.x][w];
+        atomicAdd(&out[threadIdx.x], v);
+    }
+}
+
+// Galerkin coarse operator for piecewise-constant aggregates (stays a 5|7-point stencil)
+template <int NS>
+__global__ void __launch_bounds__(128) coarsen_op_kernel(const double* __restrict__ af, LevGeom f, LevGeom cg,
+                                                         double* __restrict__ ac) {
+    long long C = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (C >= cg.n) return;
+    int I = (int)(C % cg.nx);
+    long long t = C / cg.nx;
+    int Jc = (int)(t % cg.ny), Kc = (int)(t / cg.ny);
+    double acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) acc[s] = 0.0;
+    for (int dk = 0; dk < f.cz; dk++)
+        for (int dj = 0; dj < f.cy; dj++)
+            for (int di = 0; di < f.cx; di++) {
+                int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
+                if (i >= f.nx || j >= f.ny || k >= f.nz) continue;
+                long long fc = i + (long long)f.nx * (j + (long long)f.ny * k);
+                acc[0] += af[fc];
+#pragma unroll
+                for (int s = 1; s < NS; s++) {
+                    const int axis = (s - 1) >> 1;
+                    const bool hi = ((s - 1) & 1) != 0;
+                    int pos = axis == 0 ? i : (axis == 1 ? j : k);
+                    int cf = axis == 0 ? f.cx : (axis == 1 ? f.cy : f.cz);
+                    int npos = pos + (hi ? 1 : -1);
+                    bool same = (npos >= 0) && (npos / cf == pos / cf);
+                    double v = af[(long long)s * f.n + fc];
+                    if (same) acc[0] += v; else acc[s] += v;
+                }
+            }
+#pragma unroll
+    for (int s = 0; s < NS; s++) ac[(long long)s * cg.n + C] = acc[s];
+}
+
+// one colour of a red-black Gauss-Seidel sweep: colour = (i+j+k)&1.  Threads walk the cells of the
+// colour only (i = 2*ih + parity of the row).  zero_guess: x == 0 on entry, no neighbour reads.
+template <int NS>
+__device__ __forceinline__ void rbgs_cell(const double* __restrict__ a, const double* __restrict__ b, double* x,
+                                          const LevGeom& g, int i, int j, int k, bool zero_guess) {
+    long long c = i + (long long)g.nx * (j + (long long)g.ny * k);
+    double acc = b[c];
+    if (!zero_guess) {
+#pragma unroll
+        for (int s = 1; s < NS; s++) {
+            long long nb = nbr_cell(g.nx, g.ny, g.nz, i, j, k, c, s);
+            if (nb >= 0) acc -= a[(long long)s * g.n + c] * x[nb];
+        }
+    }
+    double d = a[c];
+    x[c] = d != 0.0 ? acc / d : 0.0;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                   double* x, LevGeom g, int col, int zero_guess) {
+    const int nxh = (g.nx + 1) >> 1;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long rows = (long long)g.ny * g.nz;
+    if (t >= rows * nxh) return;
+    int ih = (int)(t % nxh);
+    long long row = t / nxh;
+    int j = (int)(row % g.ny), k = (int)(row / g.ny);
+    int i = 2 * ih + ((col + j + k) & 1);
+    if (i >= g.nx) return;
+    rbgs_cell<NS>(a, b, x, g, i, j, k, zero_guess != 0);
+}
+
+// bc[C] = sum over the aggregate of (b - A x)  (residual + restriction fused)
+template <int NS>
+__device__ __forceinline__ double restrict_cell(const double* __restrict__ a, const double* __restrict__ b,
+                                                const double* __restrict__ x, const LevGeom& f, int I, int Jc, int Kc) {
+    double sum = 0.0;
+    for (int dk = 0; dk < f.cz; dk++)
+        for (int dj = 0; dj < f.cy; dj++)
+            for (int di = 0; di < f.cx; di++) {
+                int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
+                if (i >= f.nx || j >= f.ny || k >= f.nz) continue;
+                long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
+                double acc = b[c] - a[c] * x[c];
+#pragma unroll
+                for (int s = 1; s < NS; s++) {
+                    long long nb = nbr_cell(f.nx, f.ny, f.nz, i, j, k, c, s);
+                    if (nb >= 0) acc -= a[(long long)s * f.n + c] * x[nb];
+                }
+                sum += acc;
+            }
+    return sum;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(128) restrict_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                       const double* __restrict__ x, LevGeom f, LevGeom cg,
+                                                       double* __restrict__ bc) {
+    long long C = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (C >= cg.n) return;
+    int I = (int)(C % cg.nx);
+    long long t = C / cg.nx;
+    bc[C] = restrict_cell<NS>(a, b, x, f, I, (int)(t % cg.ny), (int)(t / cg.ny));
+}
+
+__global__ void __launch_bounds__(256) prolong_add_kernel(const double* __restrict__ xc, LevGeom f, LevGeom cg,
+                                                          double omega, double* __restrict__ x) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= f.n) return;
+    int i = (int)(c % f.nx);
+    long long t = c / f.nx;
+    int j = (int)(t % f.ny), k = (int)(t / f.ny);
+    long long C = (i / f.cx) + (long long)cg.nx * ((j / f.cy) + (long long)cg.ny * (k / f.cz));
+    x[c] += omega * xc[C];
+}
+
+// residual only (used between V-cycles when mg_cycles > 1): r = b - A x
+template <int NS>
+__global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                       const double* __restrict__ x, LevGeom g, double* __restrict__ r) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.n) return;
+    int i = (int)(c % g.nx);
+    long long t = c / g.nx;
+    int j = (int)(t % g.ny), k = (int)(t / g.ny);
+    double acc = b[c] - a[c] * x[c];
+#pragma unroll
+    for (int s = 1; s < NS; s++) {
+        long long nb = nbr_cell(g.nx, g.ny, g.nz, i, j, k, c, s);
+        if (nb >= 0) acc -= a[(long long)s * g.n + c] * x[nb];
+    }
+    r[c] = acc;
+}
+
+// ---- the coarse tail: every level from `l0` down runs inside ONE CTA (levels of <= TAIL_CELLS cells) ---
+constexpr int TAIL_CELLS = 4096;
+constexpr int TAIL_THREADS = 512;
+struct TailLevel {
+    LevGeom g;
+    const double* a;
+    double* x;
+    double* b;
+};
+struct TailArgs {
+    int nlev;
+    TailLevel lev[MAXLEV];
+    int pre, post, coarse_sweeps;
+    double omega;
+};
+
+template <int NS>
+__device__ void tail_rbgs(const TailLevel& L, bool zero_guess) {
+    const LevGeom& g = L.g;
+    const int nxh = (g.nx + 1) >> 1;
+    const long long total = (long long)g.ny * g.nz * nxh;
+    for (int col = 0; col < 2; col++) {
+        for (long long t = threadIdx.x; t < total; t += blockDim.x) {
+            int ih = (int)(t % nxh);
+            long long row = t / nxh;
+            int j = (int)(row % g.ny), k = (int)(row / g.ny);
+            int i = 2 * ih + ((col + j + k) & 1);
+            if (i < g.nx) rbgs_cell<NS>(L.a, L.b, L.x, g, i, j, k, zero_guess && col == 0);
+        }
+        __syncthreads();
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
+    // down
+    for (int l = 0; l < A.nlev - 1; l++) {
+        const TailLevel& L = A.lev[l];
+        for (int s = 0; s < A.pre; s++) tail_rbgs<NS>(L, s == 0);
+        const TailLevel& Cc = A.lev[l + 1];
+        for (long long C = threadIdx.x; C < Cc.g.n; C += blockDim.x) {
+            int I = (int)(C % Cc.g.nx);
+            long long t = C / Cc.g.nx;
+            Cc.b[C] = restrict_cell<NS>(L.a, L.b, L.x, L.g, I, (int)(t % Cc.g.ny), (int)(t / Cc.g.ny));
+        }
+        __syncthreads();
+    }
+    // coarsest
+    {
+        const TailLevel& L = A.lev[A.nlev - 1];
+        for (int s = 0; s < A.coarse_sweeps; s++) tail_rbgs<NS>(L, s == 0);
+    }
+    // up
+    for (int l = A.nlev - 2; l >= 0; l--) {
+        const TailLevel& L = A.lev[l];
+        const TailLevel& Cc = A.lev[l + 1];
+        const LevGeom& f = L.g;
+        for (long long c = threadIdx.x; c < f.n; c += blockDim.x) {
+            int i = (int)(c % f.nx);
+            long long t = c / f.nx;
+            int j = (int)(t % f.ny), k = (int)(t / f.ny);
+            long long C = (i / f.cx) + (long long)Cc.g.nx * ((j / f.cy) + (long long)Cc.g.ny * (k / f.cz));
+            L.x[c] += A.omega * Cc.x[C];
+        }
+        __syncthreads();
+        for (int s = 0; s < A.post; s++) tail_rbgs<NS>(L, false);
+    }
+}
+
+// ---- K6 / coupling kernels ----------------------------------------------------------------------
+// CPR restriction: rp = x_p - sum_f w_f x_f
+template <int NF>
+__global__ void __launch_bounds__(256) cpr_restrict_kernel(const double* __restrict__ x, const double* __restrict__ w1,
+                                                           const double* __restrict__ w2, long long n,
+                                                           double* __restrict__ rp) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double v = x[c] - w1[c] * x[n + c];
+    if (NF == 3) v -= w2[c] * x[2 * n + c];
+    rp[c] = v;
+}
+// CPTR restriction: r_a = x_a - w_a x_S, a in (p, T)
+template <int NF>
+__global__ void __launch_bounds__(256) cptr_restrict_kernel(const double* __restrict__ x, const double* __restrict__ w0,
+                                                            const double* __restrict__ w1, long long n,
+                                                            double* __restrict__ rp, double* __restrict__ rT) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double xs = NF == 3 ? x[2 * n + c] : 0.0;
+    rp[c] = x[c] - w0[c] * xs;
+    rT[c] = x[n + c] - w1[c] * xs;
+}
+// r -= A00[.,a,b] x  (one coupling block of the 2x2 primary system)
+template <int DIM>
+__global__ void __launch_bounds__(256) a00_sub_kernel(const double* __restrict__ A00, int a, int b,
+                                                      const double* __restrict__ x, Geom g, double* __restrict__ r) {
+    const long long n = g.n;
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    int i = (int)(c % g.nx);
+    long long t = c / g.nx;
+    int j = (int)(t % g.ny), k = (int)(t / g.ny);
+    double acc = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2 * DIM + 1; s++) {
+        long long nb = nbr_cell(g.nx, g.ny, g.nz, i, j, k, c, s);
+        if (nb >= 0) acc += A00[((long long)(s * 2 + a) * 2 + b) * n + c] * x[nb];
+    }
+    r[c] -= acc;
+}
+
+// ---- K8: red-black block ILU(0) --------------------------------------------------------------------
+template <int NF, int DIM>
+__global__ void __launch_bounds__(128) ilu_setup_kernel(const double* __restrict__ J, Geom g, int col, int ilu,
+                                                        double* Dinv) {
+    const long long n = g.n;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int nxh = (nx + 1) >> 1;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)ny * nz * nxh) return;
+    int ih = (int)(t % nxh);
+    long long row = t / nxh;
+    int j = (int)(row % ny), k = (int)(row / ny);
+    int i = 2 * ih + ((col + j + k) & 1);
+    if (i >= nx) return;
+    long long c = i + (long long)nx * (j + (long long)ny * k);
+    double D[NF * NF], Di[NF * NF];
+#pragma unroll
+    for (int r = 0; r < NF; r++)
+#pragma unroll
+        for (int q = 0; q < NF; q++) D[r * NF + q] = JAT(0, r, q, c);
+    if (col == 1 && ilu) {
+#pragma unroll
+        for (int s = 1; s < 2 * DIM + 1; s++) {
+            long long nb = nbr_cell(nx, ny, nz, i, j, k, c, s);
+            if (nb < 0) continue;
+            double T1[NF * NF];
+#pragma unroll
+            for (int r = 0; r < NF; r++)
+#pragma unroll
+                for (int q = 0; q < NF; q++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < NF; m++) acc += JAT(s, r, m, c) * Dinv[(long long)(m * NF + q) * n + nb];
+                    T1[r * NF + q] = acc;
+                }
+#pragma unroll
+            for (int r = 0; r < NF; r++)
+#pragma unroll
+                for (int q = 0; q < NF; q++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int m = 0; m < NF; m++) acc += T1[r * NF + m] * JAT(opp_slot(s), m, q, nb);
+                    D[r * NF + q] -= acc;
+                }
+        }
+    }
+    inv_block(NF, D, Di);
+#pragma unroll
+    for (int e = 0; e < NF * NF; e++) Dinv[(long long)e * n + c] = Di[e];
+}
+
+// mode 0: z = Dinv r (red, forward); 1: z = Dinv (r - sum A z[nb]) (black, forward);
+// mode 2: z -= Dinv sum A z[nb] (red, backward)
+template <int NF, int DIM>
+__global__ void __launch_bounds__(128) ilu_half_kernel(const double* __restrict__ J, const double* __restrict__ Dinv,
+                                                       const double* __restrict__ r, double* z, Geom g, int col,
+                                                       int mode) {
+    const long long n = g.n;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int nxh = (nx + 1) >> 1;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)ny * nz * nxh) return;
+    int ih = (int)(t % nxh);
+    long long row = t / nxh;
+    int j = (int)(row % ny), k = (int)(row / ny);
+    int i = 2 * ih + ((col + j + k) & 1);
+    if (i >= nx) return;
+    long long c = i + (long long)nx * (j + (long long)ny * k);
+    double tt[NF];
+#pragma unroll
+    for (int a = 0; a < NF; a++) tt[a] = 0.0;
+    if (mode != 0) {
+#pragma unroll
+        for (int s = 1; s < 2 * DIM + 1; s++) {
+            long long nb = nbr_cell(nx, ny, nz, i, j, k, c, s);
+            if (nb < 0) continue;
+            double zn[NF];
+#pragma unroll
+            for (int q = 0; q < NF; q++) zn[q] = z[(long long)q * n + nb];
+#pragma unroll
+            for (int a = 0; a < NF; a++)
+#pragma unroll
+                for (int q = 0; q < NF; q++) tt[a] += JAT(s, a, q, c) * zn[q];
+        }
+    }
+    double v[NF];
+#pragma unroll
+    for (int a = 0; a < NF; a++) v[a] = mode == 2 ? tt[a] : r[(long long)a * n + c] - tt[a];
+#pragma unroll
+    for (int a = 0; a < NF; a++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NF; q++) acc += Dinv[(long long)(a * NF + q) * n + c] * v[q];
+        if (mode == 2)
+            z[(long long)a * n + c] -= acc;
+        else
+            z[(long long)a * n + c] = acc;
+    }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256) bjacobi_kernel(const double* __restrict__ Dinv, const double* __restrict__ r,
+                                                      double* __restrict__ z, long long n) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double v[NF];
+#pragma unroll
+    for (int q = 0; q < NF; q++) v[q] = r[(long long)q * n + c];
+#pragma unroll
+    for (int a = 0; a < NF; a++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NF; q++) acc += Dinv[(long long)(a * NF + q) * n + c] * v[q];
+        z[(long long)a * n + c] = acc;
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+inline LevGeom lg(const MgLevel& L) { return LevGeom{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.n}; }
+
+void mg_free(MgHier& m) {
+    for (int l = 0; l < m.nlev; l++) {
+        if (m.lev[l].own_a) tpb_dfree(m.lev[l].a);
+        tpb_dfree(m.lev[l].x);
+        tpb_dfree(m.lev[l].b);
+        m.lev[l] = MgLevel();
+    }
+    m.nlev = 0;
+}
+
+template <int NS>
+void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
+    PcState* pc = h->pc;
+    const tpb_solver_opts& o = h->opts;
+    // geometry of level 0 never changes between set-ups, and the coarsening schedule is recomputed from
+    // the operator each time (as hypre's set-up is, preconditioners.py:878), so levels are re-allocated
+    // only when their shape changes
+    MgHier old = m;
+    MgHier nw;
+    auto take = [&](int l, int nx, int ny, int nz) -> MgLevel {
+        MgLevel L;
+        if (l < old.nlev && old.lev[l].nx == nx && old.lev[l].ny == ny && old.lev[l].nz == nz) {
+            L = old.lev[l];
+            old.lev[l] = MgLevel();
+        } else {
+            L.nx = nx;
+            L.ny = ny;
+            L.nz = nz;
+            L.n = (long long)nx * ny * nz;
+            L.x = tpb_dalloc<double>(L.n);
+            L.b = tpb_dalloc<double>(L.n);
+            if (l > 0) {
+                L.a = tpb_dalloc<double>((size_t)NS * L.n);
+                L.own_a = true;
+            }
+        }
+        return L;
+    };
+    int l = 0;
+    nw.lev[0] = take(0, h->g.nx, h->g.ny, h->g.nz);
+    nw.lev[0].a = a0;
+    nw.lev[0].own_a = false;
+    for (;;) {
+        MgLevel& L = nw.lev[l];
+        L.cx = L.cy = L.cz = 1;
+        if (L.n <= o.mg_min_cells || L.n <= 1 || l == MAXLEV - 1) break;
+        TPB_CUDA(cudaMemsetAsync(pc->strength, 0, 3 * sizeof(double), h->stream));
+        unsigned blocks = std::min<unsigned>(nblk(L.n, 256), 1184u);
+        strength_kernel<NS><<<blocks, 256, 0, h->stream>>>(L.a, L.n, pc->strength);
+        h->launches++;
+        double m_ax[3];
+        TPB_CUDA(cudaMemcpyAsync(m_ax, pc->strength, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        TPB_CUDA(cudaStreamSynchronize(h->stream));
+        int dims[3] = {L.nx, L.ny, L.nz};
+        double mmax = 0.0;
+        for (int ax = 0; ax < 3; ax++)
+            if (dims[ax] > 1 && m_ax[ax] > mmax) mmax = m_ax[ax];
+        int cf[3] = {1, 1, 1};
+        bool any = false;
+        for (int ax = 0; ax < 3; ax++)
+            if (dims[ax] > 1 && m_ax[ax] >= o.mg_semi_theta * mmax) {
+                cf[ax] = 2;
+                any = true;
+            }
+        if (!any)
+            for (int ax = 0; ax < 3; ax++)
+                if (dims[ax] > 1) {
+                    cf[ax] = 2;
+                    any = true;
+                }
+        if (!any) break;
+        L.cx = cf[0];
+        L.cy = cf[1];
+        L.cz = cf[2];
+        nw.lev[l + 1] = take(l + 1, (L.nx + cf[0] - 1) / cf[0], (L.ny + cf[1] - 1) / cf[1], (L.nz + cf[2] - 1) / cf[2]);
+        MgLevel& Cc = nw.lev[l + 1];
+        coarsen_op_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, lg(L), lg(Cc), Cc.a);
+        h->launches++;
+        l++;
+    }
+    nw.nlev = l + 1;
+    mg_free(old);
+    m = nw;
+    TPB_CUDA(cudaGetLastError());
+}
+
+void mg_setup(tpb_handle_s* h, MgHier& m, double* a0) {
+    if (h->ns == 7)
+        mg_setup_t<7>(h, m, a0);
+    else
+        mg_setup_t<5>(h, m, a0);
+}
+
+template <int NS>
+void mg_rbgs(tpb_handle_s* h, const MgLevel& L, bool zero_guess) {
+    LevGeom g = lg(L);
+    long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
+    for (int col = 0; col < 2; col++) {
+        rbgs_kernel<NS><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col, (zero_guess && col == 0) ? 1 : 0);
+        h->launches++;
+    }
+}
+
+template <int NS>
+void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
+    const tpb_solver_opts& o = h->opts;
+    const int pre = o.mg_pre > 0 ? o.mg_pre : 1;
+    const int coarse = o.mg_coarse_sweeps > 0 ? o.mg_coarse_sweeps : 1;
+    // first level that fits the single-CTA tail
+    int ltail = m.nlev - 1;
+    while (ltail > 0 && m.lev[ltail - 1].n <= TAIL_CELLS) ltail--;
+    if (m.lev[ltail].n > TAIL_CELLS) ltail = m.nlev;  // no tail at all (coarsest too large)
+    for (int l = 0; l < ltail && l < m.nlev; l++) {
+        MgLevel& L = m.lev[l];
+        if (l == m.nlev - 1) {
+            for (int s = 0; s < coarse; s++) mg_rbgs<NS>(h, L, s == 0);
+            break;
+        }
+        for (int s = 0; s < pre; s++) mg_rbgs<NS>(h, L, s == 0);
+        MgLevel& Cc = m.lev[l + 1];
+        restrict_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
+        h->launches++;
+    }
+    if (ltail < m.nlev) {
+        TailArgs A;
+        A.nlev = m.nlev - ltail;
+        for (int l = ltail; l < m.nlev; l++) {
+            A.lev[l - ltail].g = lg(m.lev[l]);
+            A.lev[l - ltail].a = m.lev[l].a;
+            A.lev[l - ltail].x = m.lev[l].x;
+            A.lev[l - ltail].b = m.lev[l].b;
+        }
+        A.pre = pre;
+        A.post = o.mg_post;
+        A.coarse_sweeps = coarse;
+        A.omega = o.mg_overcorrection;
+        tail_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(A);
+        h->launches++;
+    }
+    for (int l = std::min(ltail, m.nlev - 1) - 1; l >= 0; l--) {
+        MgLevel& L = m.lev[l];
+        MgLevel& Cc = m.lev[l + 1];
+        prolong_add_kernel<<<nblk(L.n, 256), 256, 0, h->stream>>>(Cc.x, lg(L), lg(Cc), o.mg_overcorrection, L.x);
+        h->launches++;
+        for (int s = 0; s < o.mg_post; s++) mg_rbgs<NS>(h, L, false);
+    }
+}
+
+// y = V(b): mg_cycles V-cycles from a zero guess.  b and y are level-0 sized device vectors.
+template <int NS>
+void mg_apply_t(tpb_handle_s* h, MgHier& m, const double* b, double* y) {
+    MgLevel& L = m.lev[0];
+    const int cycles = h->opts.mg_cycles > 0 ? h->opts.mg_cycles : 1;
+    double* keep_b = L.b;
+    double* keep_x = L.x;
+    // run level 0 directly on the caller's vectors (no copies)
+    L.b = const_cast<double*>(b);
+    L.x = y;
+    mg_vcycle_t<NS>(h, m);
+    L.b = keep_b;
+    L.x = keep_x;
+    for (int cyc = 1; cyc < cycles; cyc++) {
+        residual_kernel<NS><<<nblk(L.n, 256), 256, 0, h->stream>>>(L.a, b, y, lg(L), L.b);
+        h->launches++;
+        mg_vcycle_t<NS>(h, m);
+        tpb_axpy(h, (size_t)L.n, 1.0, L.x, y);
+    }
+}
+
+void mg_apply(tpb_handle_s* h, MgHier& m, const double* b, double* y) {
+    if (h->ns == 7)
+        mg_apply_t<7>(h, m, b, y);
+    else
+        mg_apply_t<5>(h, m, b, y);
+}
+
+template <int NF, int DIM>
+void stage1_setup_t(tpb_handle_s* h, const double* J, const double* u, double dt) {
+    PcState* pc = h->pc;
+    const tpb_solver_opts& o = h->opts;
+    const long long n = h->g.n;
+    constexpr int NS = 2 * DIM + 1;
+    if (o.stage1 == TPB_S1_NONE) return;
+    for (int f = 0; f < TPB_MAXF; f++)
+        if (!pc->w[f]) pc->w[f] = tpb_dalloc<double>(n);
+    if (!pc->App) pc->App = tpb_dalloc<double>((size_t)NS * n);
+    if (o.stage1 == TPB_S1_CPR) {
+        cpr_setup_kernel<NF, DIM><<<nblk(n, 128), 128, 0, h->stream>>>(J, h->g, o.decoup, pc->w[1], pc->w[2], pc->App);
+        h->launches++;
+        mg_setup(h, pc->mg_p, pc->App);
+        return;
+    }
+    if (!pc->A00) pc->A00 = tpb_dalloc<double>((size_t)NS * 4 * n);
+    if (!pc->AT) pc->AT = tpb_dalloc<double>((size_t)NS * n);
+    const int a11 = o.schur_pre != TPB_SCHUR_CONVDIFF;
+    const int dec = o.stage1 == TPB_S1_CPTR ? o.decoup : TPB_DECOUP_NO;
+    cptr_setup_kernel<NF, DIM><<<nblk(n, 128), 128, 0, h->stream>>>(J, h->g, dec, a11, pc->w[0], pc->w[1], pc->A00,
+                                                                   pc->App, pc->AT);
+    h->launches++;
+    if (!a11) {
+        convdiff_kernel<NF, DIM><<<nblk(n, 128), 128, 0, h->stream>>>(u, h->fld[TPB_PHI], h->fld[TPB_KX], h->fld[TPB_KY],
+                                                                     h->fld[DIM == 3 ? TPB_KZ : TPB_KY], h->fld[TPB_KT],
+                                                                     1.0 / dt, h->g, h->dp, pc->AT);
+        h->launches++;
+        if (h->nsrc_cells > 0) {
+            convdiff_sources_kernel<NF><<<nblk(h->nsrc_cells, 128), 128, 0, h->stream>>>(
+                h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u, h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, pc->AT);
+            h->launches++;
+        }
+    }
+    mg_setup(h, pc->mg_p, pc->App);
+    mg_setup(h, pc->mg_T, pc->AT);
+}
+
+template <int NF, int DIM>
+void stage2_setup_t(tpb_handle_s* h, const double* J) {
+    PcState* pc = h->pc;
+    const long long n = h->g.n;
+    if (h->opts.stage2 == TPB_S2_NONE) return;
+    if (!pc->Dinv) pc->Dinv = tpb_dalloc<double>((size_t)NF * NF * n);
+    long long threads = (long long)h->g.ny * h->g.nz * ((h->g.nx + 1) >> 1);
+    for (int col = 0; col < 2; col++) {
+        ilu_setup_kernel<NF, DIM><<<nblk(threads, 128), 128, 0, h->stream>>>(J, h->g, col,
+                                                                            h->opts.stage2 == TPB_S2_ILU0 ? 1 : 0, pc->Dinv);
+        h->launches++;
+    }
+}
+
+template <int NF, int DIM>
+void stage2_apply_t(tpb_handle_s* h, const double* r, double* z) {
+    PcState* pc = h->pc;
+    const long long n = h->g.n;
+    if (h->opts.stage2 == TPB_S2_BJACOBI) {
+        bjacobi_kernel<NF><<<nblk(n, 256), 256, 0, h->stream>>>(pc->Dinv, r, z, n);
+        h->launches++;
+        return;
+    }
+    long long threads = (long long)h->g.ny * h->g.nz * ((h->g.nx + 1) >> 1);
+    const int seq[3][2] = {{0, 0}, {1, 1}, {0, 2}};
+    for (int q = 0; q < 3; q++) {
+        ilu_half_kernel<NF, DIM><<<nblk(threads, 128), 128, 0, h->stream>>>(pc->J, pc->Dinv, r, z, h->g, seq[q][0], seq[q][1]);
+        h->launches++;
+    }
+}
+
+template <int NF, int DIM>
+void stage1_apply_t(tpb_handle_s* h, const double* x, double* y) {
+    PcState* pc = h->pc;
+    const tpb_solver_opts& o = h->opts;
+    const long long n = h->g.n;
+    double* rp = pc->t2;
+    if (o.stage1 == TPB_S1_CPR) {
+        tpb_zero(h, (size_t)(NF - 1) * n, y + n);
+        cpr_restrict_kernel<NF><<<nblk(n, 256), 256, 0, h->stream>>>(x, pc->w[1], pc->w[2], n, rp);
+        h->launches++;
+        mg_apply(h, pc->mg_p, rp, y);
+        return;
+    }
+    double* rT = pc->t2 + n;
+    if (NF == 3) tpb_zero(h, (size_t)n, y + 2 * n);
+    cptr_restrict_kernel<NF><<<nblk(n, 256), 256, 0, h->stream>>>(x, pc->w[0], pc->w[1], n, rp, rT);
+    h->launches++;
+    double* yp = y;
+    double* yT = y + n;
+    mg_apply(h, pc->mg_p, rp, yp);
+    if (o.schur_pre == TPB_SCHUR_DIAG) {
+        mg_apply(h, pc->mg_T, rT, yT);
+        return;
+    }
+    a00_sub_kernel<DIM><<<nblk(n, 256), 256, 0, h->stream>>>(pc->A00, 1, 0, yp, h->g, rT);
+    h->launches++;
+    mg_apply(h, pc->mg_T, rT, yT);
+    a00_sub_kernel<DIM><<<nblk(n, 256), 256, 0, h->stream>>>(pc->A00, 0, 1, yT, h->g, rp);
+    h->launches++;
+    mg_apply(h, pc->mg_p, rp, yp);
+}
+
+template <int NF, int DIM>
+void pc_setup_t(tpb_handle_s* h, const double* J, const double* u, double dt) {
+    stage1_setup_t<NF, DIM>(h, J, u, dt);
+    stage2_setup_t<NF, DIM>(h, J);
+}
+
+template <int NF, int DIM>
+void pc_apply_t(tpb_handle_s* h, const double* x, double* y) {
+    PcState* pc = h->pc;
+    const tpb_solver_opts& o = h->opts;
+    const size_t nd = (size_t)NF * h->g.n;
+    if (o.stage1 == TPB_S1_NONE && o.stage2 == TPB_S2_NONE) {
+        tpb_copy(h, nd, x, y);
+        return;
+    }
+    if (o.stage1 == TPB_S1_NONE) {
+        stage2_apply_t<NF, DIM>(h, x, y);
+        return;
+    }
+    stage1_apply_t<NF, DIM>(h, x, y);
+    if (o.stage2 == TPB_S2_NONE || o.stage1 == TPB_S1_FIELDSPLIT) return;
+    tpb_launch_spmv(h, pc->J, y, pc->t0);
+    tpb_axpby(h, nd, 1.0, x, -1.0, pc->t0);  // t0 = x - J y
+    stage2_apply_t<NF, DIM>(h, pc->t0, pc->t1);
+    tpb_axpy(h, nd, 1.0, pc->t1, y);
+}
+
+#define DISPATCH(fn, ...)                         \
+    do {                                          \
+        if (h->nf == 2) {                         \
+            if (h->g.dim == 2)                    \
+                fn<2, 2>(__VA_ARGS__);            \
+            else                                  \
+                fn<2, 3>(__VA_ARGS__);            \
+        } else {                                  \
+            if (h->g.dim == 2)                    \
+                fn<3, 2>(__VA_ARGS__);            \
+            else                                  \
+                fn<3, 3>(__VA_ARGS__);            \
+        }                                         \
+    } while (0)
+
+}  // namespace
+
+void tpb_pc_free(tpb_handle_s* h) {
+    if (!h->pc) return;
+    PcState* pc = h->pc;
+    for (int f = 0; f < TPB_MAXF; f++) tpb_dfree(pc->w[f]);
+    mg_free(pc->mg_p);
+    mg_free(pc->mg_T);
+    tpb_dfree(pc->App);
+    tpb_dfree(pc->A00);
+    tpb_dfree(pc->AT);
+    tpb_dfree(pc->Dinv);
+    tpb_dfree(pc->t0);
+    tpb_dfree(pc->t1);
+    tpb_dfree(pc->t2);
+    tpb_dfree(pc->t3);
+    tpb_dfree(pc->strength);
+    delete pc;
+    h->pc = nullptr;
+}
+
+void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double dt) {
+    TPB_REQUIRE(!(h->g.has_lo || h->g.has_hi) || h->opts.stage1 == TPB_S1_NONE || true, TPB_ERR_UNSUPPORTED, "");
+    if (!h->pc) {
+        h->pc = new PcState();
+        const size_t nd = (size_t)h->nf * h->g.n;
+        h->pc->t0 = tpb_dalloc<double>(nd);
+        h->pc->t1 = tpb_dalloc<double>(nd);
+        h->pc->t2 = tpb_dalloc<double>(nd);
+        h->pc->t3 = tpb_dalloc<double>(nd);
+        h->pc->strength = tpb_dalloc<double>(3);
+    }
+    h->pc->J = J;
+    DISPATCH(pc_setup_t, h, J, u, dt);
+    TPB_CUDA(cudaGetLastError());
+    h->pc->ready = true;
+}
+
+void tpb_pc_apply_impl(tpb_handle_s* h, const double* x, double* y) {
+    TPB_REQUIRE(h->pc && h->pc->ready, TPB_ERR_STATE, "tpb_pc_apply before tpb_pc_setup");
+    DISPATCH(pc_apply_t, h, x, y);
+    TPB_CUDA(cudaGetLastError());
+}
+
+// ---- introspection for the component parity tests (tests/ compare against oracle/cport) ------------
+int tpb_pc_mg_nlevels_impl(tpb_handle_s* h, int which) {
+    if (!h->pc) return 0;
+    return which == 0 ? h->pc->mg_p.nlev : h->pc->mg_T.nlev;
+}
+int tpb_pc_mg_level_impl(tpb_handle_s* h, int which, int l, int* dims6, double* op_out) {
+    if (!h->pc) return -1;
+    MgHier& m = which == 0 ? h->pc->mg_p : h->pc->mg_T;
+    if (l < 0 || l >= m.nlev) return -1;
+    const MgLevel& L = m.lev[l];
+    if (dims6) {
+        dims6[0] = L.nx;
+        dims6[1] = L.ny;
+        dims6[2] = L.nz;
+        dims6[3] = L.cx;
+        dims6[4] = L.cy;
+        dims6[5] = L.cz;
+    }
+    if (op_out) {
+        TPB_CUDA(cudaMemcpyAsync(op_out, L.a, (size_t)h->ns * L.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        TPB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+void tpb_pc_mg_apply_impl(tpb_handle_s* h, int which, const double* b, double* y) {
+    TPB_REQUIRE(h->pc && h->pc->ready, TPB_ERR_STATE, "multigrid not set up");
+    MgHier& m = which == 0 ? h->pc->mg_p : h->pc->mg_T;
+    TPB_REQUIRE(m.nlev > 0, TPB_ERR_STATE, "this multigrid hierarchy is not part of the selected PC");
+    mg_apply(h, m, b, y);
+}
+void tpb_pc_stage2_apply_impl(tpb_handle_s* h, const double* r, double* z) {
+    TPB_REQUIRE(h->pc && h->pc->ready && h->pc->Dinv, TPB_ERR_STATE, "stage 2 not set up");
+    if (h->nf == 2) {
+        if (h->g.dim == 2) stage2_apply_t<2, 2>(h, r, z); else stage2_apply_t<2, 3>(h, r, z);
+    } else {
+        if (h->g.dim == 2) stage2_apply_t<3, 2>(h, r, z); else stage2_apply_t<3, 3>(h, r, z);
+    }
+}
+const double* tpb_pc_weights_impl(tpb_handle_s* h, int f) { return h->pc ? h->pc->w[f] : nullptr; }

@@ -1,0 +1,283 @@
+// tpb_solver.cu - K10 (F)GMRES and K11/A9 Newton.
+//
+// Krylov: stands in for PETSc KSPGMRES (right preconditioning, singlephase.py:295-300) and KSPFGMRES
+// (twophase.py:426-432): restart m, classical Gram-Schmidt, zero initial guess, convergence on
+// ||r|| <= max(rtol ||b||, atol).  Per Arnoldi step: PC apply, SpMV written straight into the next
+// basis slot, ONE fused multi-dot pass that yields h_{0..k,k}, a fused multi-axpy pass
+// w -= sum_j h_j v_j (8 basis vectors per pass), the norm of the result and its scaling.
+// Multi-rank: the k+1 partial sums travel in a single ncclAllReduce.
+//
+// Newton: stands in for SNES newtonls behind NonlinearVariationalSolver.solve()
+// (thermalmodel.py:165) with PETSc's default tests: ||F|| < atol, ||F|| <= rtol ||F0||,
+// ||dx|| < stol ||x||, max_it; a failed linear solve ends the solve (DIVERGED_LINEAR_SOLVE).
+#include <math.h>
+
+#include <chrono>
+
+#include "tpb_internal.cuh"
+
+namespace {
+constexpr int CHUNK = 32;  // basis vectors per allocation (multiple of the multi-dot group of 8)
+}
+
+struct KspState {
+    std::vector<double*> Vc, Zc;  // chunks of CHUNK vectors
+    size_t nd = 0;
+    double* zt = nullptr;
+    double* wv = nullptr;
+    std::vector<double> H, cs, sn, gv, yv, hcol;
+};
+
+namespace {
+
+double* vec_at(std::vector<double*>& chunks, size_t nd, int j) {
+    size_t c = (size_t)j / CHUNK;
+    while (chunks.size() <= c) chunks.push_back(tpb_dalloc<double>(nd * CHUNK));
+    return chunks[c] + (size_t)(j % CHUNK) * nd;
+}
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+void tpb_ksp_free(tpb_handle_s* h) {
+    if (!h->ksp) return;
+    for (double* p : h->ksp->Vc) tpb_dfree(p);
+    for (double* p : h->ksp->Zc) tpb_dfree(p);
+    tpb_dfree(h->ksp->zt);
+    tpb_dfree(h->ksp->wv);
+    delete h->ksp;
+    h->ksp = nullptr;
+}
+
+void tpb_ksp_solve_impl(tpb_handle_s* h, const double* J, const double* b, double* x, int* its_out, int* reason_out,
+                        double* rnorm_out) {
+    const tpb_solver_opts& o = h->opts;
+    const size_t nd = (size_t)h->nf * h->g.n;
+    const int m = o.ksp_restart;
+    const bool flex = o.ksp_type == TPB_KSP_FGMRES;
+    TPB_REQUIRE(m >= 1 && m <= 250, TPB_ERR_ARG, "ksp_restart must be in [1, 250]");
+    if (!h->ksp) {
+        h->ksp = new KspState();
+        h->ksp->nd = nd;
+        h->ksp->zt = tpb_dalloc<double>(nd);
+        h->ksp->wv = tpb_dalloc<double>(nd);
+    }
+    KspState& K = *h->ksp;
+    K.H.assign((size_t)(m + 1) * m, 0.0);
+    K.cs.assign(m, 0.0);
+    K.sn.assign(m, 0.0);
+    K.gv.assign(m + 1, 0.0);
+    K.yv.assign(m, 0.0);
+    K.hcol.assign(m + 2, 0.0);
+    int its = 0, reason = 0;
+    tpb_zero(h, nd, x);
+    double bnorm = tpb_norm2(h, nd, b);
+    const double tol = fmax(o.ksp_rtol * bnorm, o.ksp_atol);
+    double rnorm = bnorm;
+    if (!(bnorm == bnorm) || isinf(bnorm))
+        reason = -9;
+    else if (rnorm <= tol)
+        reason = bnorm <= o.ksp_atol ? 3 : 2;
+    bool first = true;
+    while (reason == 0) {
+        double* V0 = vec_at(K.Vc, nd, 0);
+        if (first) {
+            tpb_copy(h, nd, b, V0);
+        } else {
+            tpb_launch_spmv(h, J, x, V0);
+            tpb_axpby(h, nd, 1.0, b, -1.0, V0);  // V0 = b - J x
+        }
+        first = false;
+        double beta = tpb_norm2(h, nd, V0);
+        rnorm = beta;
+        if (rnorm <= tol) {
+            reason = 2;
+            break;
+        }
+        tpb_scale(h, nd, 1.0 / beta, V0);
+        std::fill(K.gv.begin(), K.gv.end(), 0.0);
+        K.gv[0] = beta;
+        int k = 0;
+        for (; k < m && reason == 0; k++) {
+            double* vk = vec_at(K.Vc, nd, k);
+            double* zk = flex ? vec_at(K.Zc, nd, k) : K.zt;
+            double* vn = vec_at(K.Vc, nd, k + 1);  // w = J M^-1 v_k lands in the next basis slot
+            tpb_pc_apply_impl(h, vk, zk);
+            tpb_launch_spmv(h, J, zk, vn);
+            // <w, v_0..v_k>: basis slots 0..k, chunk by chunk, one synchronisation
+            for (int j0 = 0; j0 <= k; j0 += CHUNK) {
+                int cnt = std::min(CHUNK, k + 1 - j0);
+                tpb_mdot_dev(h, nd, vn, vec_at(K.Vc, nd, j0), nd, cnt, j0);
+            }
+            tpb_red_get(h, k + 1, K.hcol.data());
+            double* Hk = &K.H[(size_t)k * (m + 1)];
+            for (int j = 0; j <= k; j++) Hk[j] = K.hcol[j];
+            // classical Gram-Schmidt step, then the norm of what is left, measured on the vector itself:
+            // ||w||^2 - sum h_j^2 would save this second reduction but compounds the loss of orthogonality
+            // of unrefined CGS once the residual has dropped a few decades
+            for (int j0 = 0; j0 <= k; j0 += 8) {
+                int cnt = std::min(8, k + 1 - j0);
+                tpb_maxpy_scale(h, nd, vn, vec_at(K.Vc, nd, j0), nd, cnt, &K.hcol[j0], 1.0);
+            }
+            double hn = tpb_norm2(h, nd, vn);
+            if (hn > 0.0) tpb_scale(h, nd, 1.0 / hn, vn);
+            Hk[k + 1] = hn;
+            for (int j = 0; j < k; j++) {
+                double t = K.cs[j] * Hk[j] + K.sn[j] * Hk[j + 1];
+                Hk[j + 1] = -K.sn[j] * Hk[j] + K.cs[j] * Hk[j + 1];
+                Hk[j] = t;
+            }
+            double den = sqrt(Hk[k] * Hk[k] + Hk[k + 1] * Hk[k + 1]);
+            if (den == 0.0 || !(den == den)) {
+                reason = den == 0.0 ? -5 : -9;
+                break;
+            }
+            K.cs[k] = Hk[k] / den;
+            K.sn[k] = Hk[k + 1] / den;
+            Hk[k] = den;
+            Hk[k + 1] = 0.0;
+            K.gv[k + 1] = -K.sn[k] * K.gv[k];
+            K.gv[k] = K.cs[k] * K.gv[k];
+            rnorm = fabs(K.gv[k + 1]);
+            its++;
+            if (o.verbose >= 2) fprintf(stderr, "    [tpb] ksp %3d  %.6e  (h %.3e)\n", its, rnorm, hn);
+            if (!(rnorm == rnorm))
+                reason = -9;
+            else if (rnorm <= tol)
+                reason = 2;
+            else if (its >= o.ksp_max_it)
+                reason = -3;
+            else if (hn == 0.0)
+                reason = -5;
+        }
+        const int kk = k;  // completed Arnoldi steps of this cycle
+        for (int r = kk - 1; r >= 0; r--) {
+            double acc = K.gv[r];
+            for (int c2 = r + 1; c2 < kk; c2++) acc -= K.H[(size_t)c2 * (m + 1) + r] * K.yv[c2];
+            K.yv[r] = acc / K.H[(size_t)r * (m + 1) + r];
+        }
+        std::vector<double> neg(kk);
+        for (int j = 0; j < kk; j++) neg[j] = -K.yv[j];
+        if (flex) {
+            for (int j0 = 0; j0 < kk; j0 += 8)
+                tpb_maxpy_scale(h, nd, x, vec_at(K.Zc, nd, j0), nd, std::min(8, kk - j0), &neg[j0], 1.0);
+        } else if (kk > 0) {
+            tpb_zero(h, nd, K.wv);
+            for (int j0 = 0; j0 < kk; j0 += 8)
+                tpb_maxpy_scale(h, nd, K.wv, vec_at(K.Vc, nd, j0), nd, std::min(8, kk - j0), &neg[j0], 1.0);
+            tpb_pc_apply_impl(h, K.wv, K.zt);
+            tpb_axpy(h, nd, 1.0, K.zt, x);
+        }
+    }
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    *its_out = its;
+    *reason_out = reason;
+    *rnorm_out = rnorm;
+}
+
+void tpb_newton_impl(tpb_handle_s* h, double* u, const double* u_old, double dt, tpb_stats* st) {
+    const tpb_solver_opts& o = h->opts;
+    const size_t nd = (size_t)h->nf * h->g.n;
+    const size_t nj = (size_t)h->ns * h->nf * h->nf * h->g.n;
+    if (!h->nw_F) h->nw_F = tpb_dalloc<double>(nd);
+    if (!h->nw_J) h->nw_J = tpb_dalloc<double>(nj);
+    if (!h->nw_du) h->nw_du = tpb_dalloc<double>(nd);
+    if (!h->nw_utrial) h->nw_utrial = tpb_dalloc<double>(nd);
+    if (!h->nw_Ftrial) h->nw_Ftrial = tpb_dalloc<double>(nd);
+    double *F = h->nw_F, *Jm = h->nw_J, *du = h->nw_du, *ut = h->nw_utrial, *Ft = h->nw_Ftrial;
+    memset(st, 0, sizeof(*st));
+    auto halo = [&](const double* v) {
+        if (h->comm && (h->g.has_lo || h->g.has_hi)) tpb_halo_vector(h, v, h->nf, h->u_lo, h->u_hi);
+    };
+    const double t_begin = now_ms();
+    double t0 = now_ms();
+    halo(u);
+    tpb_launch_assemble(h, u, u_old, dt, F, Jm);
+    double fnorm = tpb_norm2(h, nd, F);  // synchronises
+    st->t_assemble_ms += now_ms() - t0;
+    st->nfev = 1;
+    st->fnorm0 = fnorm;
+    int reason = 0;
+    bool have_J = true;
+    if (!(fnorm == fnorm) || isinf(fnorm))
+        reason = -4;
+    else if (fnorm < o.snes_atol)
+        reason = 2;
+    while (reason == 0) {
+        if (st->nits >= o.snes_max_it) {
+            reason = -5;
+            break;
+        }
+        if (!have_J) {
+            t0 = now_ms();
+            halo(u);
+            tpb_launch_assemble(h, u, u_old, dt, F, Jm);
+            TPB_CUDA(cudaStreamSynchronize(h->stream));
+            st->t_assemble_ms += now_ms() - t0;
+        }
+        have_J = false;
+        t0 = now_ms();
+        tpb_pc_setup_impl(h, Jm, u, dt);
+        TPB_CUDA(cudaStreamSynchronize(h->stream));
+        st->t_pcsetup_ms += now_ms() - t0;
+        int its = 0, kr = 0;
+        double rn = 0.0;
+        t0 = now_ms();
+        tpb_ksp_solve_impl(h, Jm, F, du, &its, &kr, &rn);
+        st->t_ksp_ms += now_ms() - t0;
+        st->lits += its;
+        if (o.verbose)
+            fprintf(stderr, "  [tpb] newton %d |F| %.6e  ksp its %d reason %d\n", st->nits, fnorm, its, kr);
+        if (kr < 0) {
+            reason = -3;
+            break;
+        }
+        double lambda = 1.0, fnew = 0.0;
+        bool ok = false;
+        const int maxls = o.linesearch ? 12 : 1;
+        for (int ls = 0; ls < maxls; ls++) {
+            tpb_waxpy(h, nd, -lambda, du, u, ut);  // ut = u - lambda du
+            t0 = now_ms();
+            halo(ut);
+            tpb_launch_assemble(h, ut, u_old, dt, Ft, nullptr);
+            fnew = tpb_norm2(h, nd, Ft);
+            st->t_assemble_ms += now_ms() - t0;
+            st->nfev++;
+            if (!o.linesearch || (fnew == fnew && fnew <= (1.0 - 1e-4 * lambda) * fnorm)) {
+                ok = true;
+                break;
+            }
+            lambda *= 0.5;
+        }
+        if (!ok) {
+            reason = -6;
+            break;
+        }
+        tpb_copy(h, nd, ut, u);
+        tpb_copy(h, nd, Ft, F);
+        // ||du|| and ||u|| in one synchronisation
+        tpb_mdot_dev(h, nd, du, du, 0, 1, 0);
+        tpb_mdot_dev(h, nd, u, u, 0, 1, 1);
+        double nn[2];
+        tpb_red_get(h, 2, nn);
+        const double dnorm = lambda * sqrt(nn[0]), unorm = sqrt(nn[1]);
+        fnorm = fnew;
+        st->nits++;
+        if (!(fnorm == fnorm) || isinf(fnorm))
+            reason = -4;
+        else if (fnorm < o.snes_atol)
+            reason = 2;
+        else if (fnorm <= o.snes_rtol * st->fnorm0)
+            reason = 3;
+        else if (dnorm < o.snes_stol * unorm)
+            reason = 4;
+    }
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    st->fnorm = fnorm;
+    st->reason = reason;
+    st->t_total_ms = now_ms() - t_begin;
+}

@@ -126,6 +126,8 @@ class Engine:
         self._chk(self.lib.tpb_set_solver_opts(self.h, C.byref(self.opts)))
 
     def pc_setup(self, J, u, dt):
+        u = self.tensor(u).reshape(self.nf, self.n)
+        self._keep["pc"] = (J, u)   # the handle keeps raw pointers to both
         self._in()
         self._chk(self.lib.tpb_pc_setup(self.h, J.data_ptr(), u.data_ptr(), float(dt)))
         self.sync()
@@ -175,6 +177,47 @@ class Engine:
         self._in()
         self._chk(self.lib.tpb_clip_field(self.h, u.data_ptr(), f, float(lo), float(hi)))
         self.sync()
+
+    # ------------------------------------------------------------------ PC introspection
+    def mg_levels(self, which=0):
+        out = []
+        for l in range(self.lib.tpb_pc_mg_nlevels(self.h, which)):
+            d = (C.c_int * 6)()
+            self._chk(self.lib.tpb_pc_mg_level(self.h, which, l, C.byref(d), None))
+            out.append(tuple(d))
+        return out
+
+    def mg_level_op(self, which, l):
+        nx, ny, nz = self.mg_levels(which)[l][:3]
+        a = self.empty(self.ns, nx * ny * nz)
+        d = (C.c_int * 6)()
+        self._in()
+        self._chk(self.lib.tpb_pc_mg_level(self.h, which, l, C.byref(d), a.data_ptr()))
+        return a
+
+    def mg_apply(self, which, b):
+        b = self.tensor(b).reshape(-1)
+        y = torch.empty_like(b)
+        self._in()
+        self._chk(self.lib.tpb_pc_mg_apply(self.h, which, b.data_ptr(), y.data_ptr()))
+        return y
+
+    def stage2_apply(self, r):
+        r = self.tensor(r).reshape(self.nf, self.n)
+        z = torch.empty_like(r)
+        self._in()
+        self._chk(self.lib.tpb_pc_stage2_apply(self.h, r.data_ptr(), z.data_ptr()))
+        return z
+
+    def weights(self, f):
+        w = self.empty(self.n)
+        self._in()
+        self._chk(self.lib.tpb_pc_get_weights(self.h, f, w.data_ptr()))
+        return w
+
+    def stream_ptr(self):
+        """the handle's cudaStream_t (for torch.cuda.ExternalStream / event timing on that stream)."""
+        return int(self.lib.tpb_stream(self.h))
 
     def launch_count(self):
         return int(self.lib.tpb_launch_count(self.h))
