@@ -1,0 +1,121 @@
+"""CPU checks of the C/OpenMP restatement (oracle/cport): pinned against the reference-form golden
+vectors (tests/golden, made by the reference's own form code), against the NumPy oracle, and - for
+the solver stack - against the golden time loops of the reference's ThermalModel.solve()."""
+import numpy as np
+import pytest
+
+from oracle import cport, tp_oracle as orc
+from tests.golden_util import golden_names, load, rel_err_rows
+from tests.gpu_util import random_problem
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_assembly_matches_reference_golden(name):
+    meta, pb, z = load(name)
+    eng = cport.engine_from_problem(pb)
+    F, J = eng.assemble(z["u"], z["u_old"], meta["dt"])
+    assert rel_err_rows(F, z["F"]) < TOL
+    assert rel_err_rows(J, z["J"]) < TOL
+    x = np.random.default_rng(0).normal(size=F.shape)
+    assert rel_err_rows(eng.spmv(J, x), orc.spmv(J, pb.grid, x)) < 1e-13
+    eng.close()
+
+
+@pytest.mark.parametrize("dim,nphase,shape", [(3, 2, (5, 7, 9)), (3, 1, (4, 6, 11)), (2, 2, (1, 9, 13)), (2, 1, (1, 8, 7))])
+def test_assembly_matches_numpy_oracle_random(dim, nphase, shape):
+    pb, u, uo = random_problem(dim, nphase, shape, seed=11)
+    eng = cport.engine_from_problem(pb)
+    F, J = eng.assemble(u, uo, 8640.0)
+    assert rel_err_rows(F, orc.residual(pb, u, uo, 8640.0)) < TOL
+    assert rel_err_rows(J, orc.jacobian(pb, u, uo, 8640.0)) < TOL
+    eng.close()
+
+
+def test_pc_is_a_fixed_linear_operator_and_reduces_the_residual():
+    pb, u, uo = random_problem(3, 2, (8, 10, 12), seed=2, spread=0.05)
+    eng = cport.engine_from_problem(pb)
+    eng.set_solver_opts(stage1=cport.S1_CPTR, decoup=1)
+    F, J = eng.assemble(u, uo, 4000.0)
+    eng.pc_setup(J, u, 4000.0)
+    rng = np.random.default_rng(1)
+    a, b = rng.normal(size=F.shape), rng.normal(size=F.shape)
+    lhs = eng.pc_apply(2.0 * a - 3.0 * b)
+    rhs = 2.0 * eng.pc_apply(a) - 3.0 * eng.pc_apply(b)
+    assert np.abs(lhs - rhs).max() < 1e-10 * np.abs(rhs).max()
+    x, its, reason, rn = eng.ksp_solve(J, F)
+    assert reason == 2 and its < 60
+    assert np.linalg.norm(eng.spmv(J, x) - F) <= 2e-8 * np.linalg.norm(F)
+    eng.close()
+
+
+def test_galerkin_coarse_operators_preserve_row_sums():
+    """piecewise-constant Galerkin: the sum of all entries of a level equals that of the level above."""
+    pb, u, uo = random_problem(3, 2, (9, 10, 11), seed=3, spread=0.05)
+    eng = cport.engine_from_problem(pb)
+    eng.set_solver_opts(stage1=cport.S1_CPR, decoup=0)
+    F, J = eng.assemble(u, uo, 4000.0)
+    eng.pc_setup(J, u, 4000.0)
+    lev = eng.mg_levels(0)
+    assert lev[0][:3] == (11, 10, 9) and lev[-1][0] * lev[-1][1] * lev[-1][2] <= 8
+    assert np.array_equal(eng.mg_level_op(0, 0), J[:, 0, 0, :])
+    tot = [eng.mg_level_op(0, l).sum() for l in range(len(lev))]
+    scale = np.abs(eng.mg_level_op(0, 0)).sum()
+    assert max(abs(t - tot[0]) for t in tot) < 1e-12 * scale
+    eng.close()
+
+
+def test_decoupling_weights_follow_the_reference_formulas():
+    """QI: diag(A_ps)/diag(A_ss) (preconditioners.py:785-808); TI: column sums (:684-711)."""
+    pb, u, uo = random_problem(2, 2, (1, 7, 9), seed=6, spread=0.05)
+    eng = cport.engine_from_problem(pb)
+    F, J = eng.assemble(u, uo, 4000.0)
+    A = orc.to_csr(J, pb.grid, "field").toarray()
+    n = pb.grid.n
+    Aps, Ass, Asp, App = A[:n, 2 * n:], A[2 * n:, 2 * n:], A[2 * n:, :n], A[:n, :n]
+    for dec, w_ref in ((1, np.diag(Aps) / np.diag(Ass)), (2, Aps.sum(axis=0) / Ass.sum(axis=0))):
+        eng.set_solver_opts(stage1=cport.S1_CPR, decoup=dec)
+        eng.pc_setup(J, u, 4000.0)
+        assert np.allclose(eng.weights(2), w_ref, rtol=1e-12, atol=0)
+        At = App - np.diag(w_ref) @ Asp
+        got = orc.to_csr(eng.mg_level_op(0, 0)[:, None, None, :], pb.grid, "field").toarray()
+        assert np.abs(got - At).max() < 1e-12 * np.abs(At).max()
+    eng.close()
+
+
+LOOPS = {
+    "l1_sp2d_homo_loop": dict(end=2.0, maxdt=1.0, small_dt_start=False, dt_init_fact=2 ** -10, spe10=False),
+    "l2_tp2d_hetero_loop": dict(end=0.02, maxdt=0.01, small_dt_start=True, dt_init_fact=2 ** -3, spe10=True),
+    "l3_tp3d_heater_loop": dict(end=3.0, maxdt=1.0, small_dt_start=False, dt_init_fact=2 ** -10, spe10=False),
+}
+
+
+class NpOps:
+    def copy(self, d, s):
+        d[...] = s
+
+    def minmax(self, u, f):
+        return float(u[f].min()), float(u[f].max())
+
+    def clip(self, u, f, lo, hi):
+        np.clip(u[f], lo, hi, out=u[f])
+
+
+@pytest.mark.parametrize("name", sorted(LOOPS))
+def test_time_loop_reproduces_reference_golden_loop(name):
+    """host time-loop logic (thermalporous_b200.model.run_time_loop) + CPU restatement against the
+    reference's own ThermalModel.solve(): same dt sequence, same Newton counts, fields to 1e-8."""
+    from thermalporous_b200.model import run_time_loop
+    meta, pb, z = load(name)
+    eng = cport.engine_from_problem(pb)
+    eng.set_solver_opts(snes_rtol=1e-12, snes_stol=1e-13, ksp_rtol=1e-10)
+    u = np.ascontiguousarray(z["u_init"], dtype=np.float64).copy()
+    uo = u.copy()
+    res = run_time_loop(lambda a, b, dt: eng.newton_solve(a, b, dt), NpOps(), u, uo, two_phase=pb.nphase == 2, i_S=2,
+                        **LOOPS[name])
+    assert np.allclose(res.dt_vec, z["loop_dts"], rtol=1e-13)
+    assert list(res.nits_vec) == [int(v) for v in z["loop_nits"]]
+    for f in range(pb.nf):
+        assert np.abs(u[f] - z["u_final"][f]).max() <= 1e-8 * np.abs(z["u_final"][f]).max()
+    eng.close()

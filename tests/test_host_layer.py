@@ -1,0 +1,145 @@
+"""Host-side mirror of the reference's geo / case / option surface (no GPU needed)."""
+import numpy as np
+import pytest
+
+from tests.golden_util import load
+from thermalporous_b200 import cases as CS, geo as G, options as O
+from thermalporous_b200.model import ConvergenceError, run_time_loop
+from thermalporous_b200.physicalparameters import PhysicalParameters
+
+
+def params(**kw):
+    class P(PhysicalParameters):
+        pass
+    p = P()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _srcs(pb):
+    return sorted((s.cell, s.kind, s.weight, s.bhp, s.max_rate, s.const_rate) for s in pb.sources)
+
+
+def test_wellcase_reproduces_reference_deltas():
+    """the golden fixtures store the delta fields the reference's WellCase built (wellcase.py:110-169)."""
+    meta, pb, z = load("g1_sp2d_homo_const")
+    prm = params(rate=1e-6, T_prod=320.0)
+    geo = G.HomogeneousGeo(10, 8, prm, 20.0, 20.0)
+    case = CS.WellCase(prm, geo, well_case="test0", constant_rate=True)
+    assert sorted(CS.source_entries(case, prm, geo)) == _srcs(pb)
+    assert np.allclose(geo.kT, 0.2 * prm.ko + 0.8 * prm.kr) and geo.name == "Homogeneous 10X8 grid"
+
+
+def test_heatercase_bump_and_duplicates():
+    meta, pb, z = load("g7_tp3d_homo_heater")
+    prm = params(rate=1e-7, T_inj=373.15, S_o=0.9)
+    geo = G.HomogeneousBoxGeo(8, 8, 8, prm, 1.2, 1.2, 4.0)
+    L = 1.2
+    hp = [[L / 4 + 0.01, L / 2 + 0.02, 0.8], [3 * L / 4, L / 2, 3.2], [L / 4 + 0.01, L / 2 + 0.02, 0.8]]
+    got = sorted(CS.source_entries(CS.HeaterCase(prm, geo, heater_points=hp), prm, geo))
+    ref = _srcs(pb)
+    assert [g[:2] for g in got] == [r[:2] for r in ref]
+    assert np.allclose([g[2] for g in got], [r[2] for r in ref], rtol=1e-13)
+
+
+def test_sourceterms_sum_coincident_points():
+    meta, pb, z = load("g6_tp3d_sources")
+    prm = params(rate=2e-4, S_o=0.8)
+
+    class HG(G.BoxGeo):
+        def generate_geo_fields(self):
+            self.phi, self.K_x, self.K_y, self.K_z, self.kT = pb.phi, pb.Kx, pb.Ky, pb.Kz, None
+    geo = HG(6, 5, 4, prm, 6 * 6.096, 5 * 3.048, 4 * 0.6096)
+    pp = [[1.5 * 6.096, 2.5 * 3.048, 0.5 * 0.6096]]
+    ip = [[4.5 * 6.096, 1.5 * 3.048, 3.5 * 0.6096]]
+    case = CS.SourceTerms(prm, geo, prod_points=pp + pp, inj_points=ip, heater_points=pp + ip)
+    assert sorted(CS.source_entries(case, prm, geo)) == _srcs(pb)
+    assert prm.prod_rate == prm.rate and case.name == "Sources"
+
+
+def test_spe10_layout_and_synthetic_statistics():
+    phi, Kx, Ky, Kz = G.spe10_synthetic(12, 20, 17, seed=10)
+    assert phi.shape == Kx.shape == (12, 20, 17)
+    prm = params()
+    geo = G.SPE10Model3D(12, 20, 17, prm, fields=(phi, Kx, Ky, Kz))
+    # slice arrays are [i, j, k]; cells are x fastest (SPE10model3D.py:30-68)
+    i, j, k = 3, 7, 11
+    c = i + 12 * (j + 20 * k)
+    assert geo.K_x[c] == Kx[i, j, k] and geo.phi[c] == phi[i, j, k] + 1e-10
+    assert (geo.Dx, geo.Dy, geo.Dz) == (6.096, 3.048, 0.6096) and geo.name.startswith("SPE10")
+    ratio = Kz / Kx
+    assert np.isclose(ratio.min(), 1e-3) and np.isclose(ratio.max(), 0.3)
+    assert Kx.min() >= 6.65e-4 * G.MD_TO_MM2 * 0.999 and Kx.max() <= 2e4 * G.MD_TO_MM2 * 1.001
+    g2 = G.SPE10Model3D(12, 20, 17, prm, fields=(phi, Kx, Ky, Kz), refine_z=3)
+    assert g2.Nz == 51 and np.isclose(g2.Dz, 0.6096 / 3) and g2.K_x[c % 240 + 240 * (3 * k + 1)] == Kx[i, j, k]
+    with pytest.raises(FileNotFoundError):
+        G.SPE10Model3D(12, 20, 17, prm, data_dir="/nonexistent")
+
+
+def test_option_sets_resolve_like_the_reference_dispatchers():
+    o, dec, _ = O.resolve("pc_cptr", 2)
+    assert (o["stage1"], o["stage2"], o["ksp_type"], o["ksp_rtol"], o["snes_max_it"]) == (O.S1_CPTR, O.S2_ILU0, O.KSP_FGMRES, 1e-8, 25)
+    o, dec, _ = O.resolve(None, 2)            # twophase.py:929-930 -> pc_cptr_gmres
+    assert o["stage1"] == O.S1_CPTR and dec == "No"
+    o, dec, _ = O.resolve("pc_cpr_TI_temp", 2)
+    assert o["stage1"] == O.S1_CPR and dec == "TI_temp"
+    o, dec, _ = O.resolve("pc_cpr_QI", 1)
+    assert (o["stage1"], o["ksp_type"], o["snes_max_it"], o["ksp_rtol"]) == (O.S1_CPR, O.KSP_GMRES, 15, 1e-5) and dec == "QI"
+    o, _, _ = O.resolve("pc_fieldsplit_cd", 1)
+    assert (o["stage1"], o["schur_pre"], o["stage2"]) == (O.S1_FIELDSPLIT, O.SCHUR_CONVDIFF, O.S2_NONE)
+    o, _, _ = O.resolve(None, 1)              # singlephase.py:412: unmatched name -> bare GMRES + default PC
+    assert o["stage1"] == O.S1_NONE and o["stage2"] == O.S2_ILU0
+    for bad in ("pc_lu", "pc_hypre", "pc_cptramg", "faspardecomp"):
+        with pytest.raises(O.UnsupportedOption):
+            O.resolve(bad, 2)
+    with pytest.raises(O.UnsupportedOption):
+        O.resolve("pc_fieldsplit_selfp", 1)
+    # the raw PETSc dict the reference's pc_cptr expands to (twophase.py:531-550) plus a decoupling key
+    v_cycle = {"ksp_type": "preonly", "pc_type": "hypre", "pc_hypre_type": "boomeramg", "pc_hypre_boomeramg_max_iter": 1}
+    d = {"snes_type": "newtonls", "snes_max_it": 25, "ksp_type": "fgmres", "ksp_max_it": 200, "ksp_gmres_restart": 200,
+         "ksp_rtol": 1e-8, "pc_type": "composite", "pc_composite_type": "multiplicative",
+         "pc_composite_pcs": "python,bjacobi", "sub_0_pc_python_type": "thermalporous.preconditioners.CPTRStage1PC",
+         "sub_0_cpr_stage1_pc_type": "fieldsplit", "sub_0_cpr_stage1_pc_fieldsplit_type": "schur",
+         "sub_0_cpr_stage1_fieldsplit_0": v_cycle, "sub_1_sub_pc_type": "ilu", "sub_1_sub_pc_factor_levels": 0,
+         "mat_type": "aij", "sub_0_cpr_decoup": "QI"}
+    o, dec, _ = O.resolve(d, 2)
+    assert o["stage1"] == O.S1_CPTR and dec == "QI" and o["ksp_restart"] == 200
+
+
+def test_time_loop_failure_halves_dt_and_restores_state():
+    """thermalmodel.py:162-181 (retry with dt/2) and :193-229 (saturation chop + clip)."""
+    calls = []
+
+    class St:
+        def __init__(self, reason, nits=3):
+            self.reason, self.nits, self.lits = reason, nits, 7
+
+    class Ops:
+        def copy(self, d, s):
+            d[...] = s
+
+        def minmax(self, u, f):
+            return float(u[f].min()), float(u[f].max())
+
+        def clip(self, u, f, lo, hi):
+            np.clip(u[f], lo, hi, out=u[f])
+    u = np.zeros((3, 4))
+    u[2] = 0.5
+    uo = u.copy()
+
+    def newton(a, b, dt):
+        calls.append(dt)
+        if len(calls) == 1:
+            a[:] = 99.0                 # garbage left behind by a failed solve must be discarded
+            return St(-3)
+        a[0] += 1.0
+        a[2] = 1.2 if len(calls) == 2 else 0.9
+        return St(3)
+    res = run_time_loop(newton, Ops(), u, uo, end=1.0, maxdt=1.0, small_dt_start=False, dt_init_fact=1.0,
+                        two_phase=True, i_S=2, spe10=False, max_steps=1)
+    assert calls == [86400.0, 43200.0, 21600.0]            # fail -> half; S > 1 -> half again (chop)
+    assert res.failed_solves == 1 and res.chops == 1 and res.dt_vec == [21600.0]
+    assert u[0, 0] == 1.0 and np.all(u[2] == 0.9) and np.array_equal(u, uo)
+    with pytest.raises(ConvergenceError):
+        raise ConvergenceError(-3)
