@@ -20,7 +20,8 @@ def test_assembly_matches_reference_golden(name):
     assert rel_err_rows(F.cpu().numpy(), z["F"]) < TOL
     assert rel_err_rows(J.cpu().numpy(), z["J"]) < TOL
     F2 = eng.assemble(z["u"], z["u_old"], meta["dt"], jacobian=False)
-    assert np.array_equal(F2.cpu().numpy(), F.cpu().numpy())
+    # the residual-only kernel is a separately compiled instantiation: same formulas, FMA contraction may differ
+    assert rel_err_rows(F2.cpu().numpy(), F.cpu().numpy()) < 1e-14
     eng.close()
 
 

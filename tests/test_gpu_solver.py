@@ -170,10 +170,23 @@ def test_free_running_time_loop_reaches_the_reference_end_state(name):
                         i_S=2, **LOOPS[name])
     assert res.t == pytest.approx(float(np.sum(z["loop_dts"])), rel=1e-12)
     same_path = len(res.dt_vec) == len(z["loop_dts"]) and np.allclose(res.dt_vec, z["loop_dts"], rtol=1e-13)
-    tol = 1e-8 if same_path else 1e-3
     final = u.cpu().numpy()
+    if same_path:
+        ref = z["u_final"]
+    else:
+        # a Newton count at the 1e-12 tolerance edge differed, so the dt heuristic took another path: compare
+        # with the CPU restatement driven through the dt sequence the GPU run actually took
+        c = cport.engine_from_problem(pb)
+        c.set_solver_opts(snes_rtol=1e-12, snes_stol=1e-13, ksp_rtol=1e-10)
+        ref = np.ascontiguousarray(z["u_init"], dtype=np.float64).copy()
+        for dt in res.dt_vec:
+            st = c.newton_solve(ref, ref.copy(), dt)
+            assert st.reason > 0
+            if pb.nphase == 2:
+                np.clip(ref[2], 0.0, 1.0, out=ref[2])
+        c.close()
     for f in range(pb.nf):
-        assert np.abs(final[f] - z["u_final"][f]).max() <= tol * np.abs(z["u_final"][f]).max()
+        assert np.abs(final[f] - ref[f]).max() <= 1e-8 * np.abs(ref[f]).max()
     g.close()
 
 

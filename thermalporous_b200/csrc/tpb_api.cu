@@ -73,6 +73,7 @@ int tpb_create(const tpb_grid* grid, int nphase, const tpb_params* prm, int devi
         g.h[0] = grid->dx;
         g.h[1] = grid->dy;
         g.h[2] = g.dim == 3 ? grid->dz : 1.0;
+        for (int a = 0; a < 3; a++) g.ih[a] = 1.0 / g.h[a];
         if (g.dim == 3) {
             g.area[0] = grid->dy * grid->dz;
             g.area[1] = grid->dx * grid->dz;
@@ -151,6 +152,9 @@ int tpb_destroy(tpb_handle h) {
     tpb_dfree(h->u_hi);
     tpb_dfree(h->x_lo);
     tpb_dfree(h->x_hi);
+    tpb_dfree(h->scr);
+    for (int a = 0; a < 3; a++) tpb_dfree(h->trans[a]);
+    tpb_dfree(h->trans_lo);
     tpb_dfree(h->src_cell);
     tpb_dfree(h->src_off);
     tpb_dfree(h->src_ent);
@@ -178,6 +182,7 @@ int tpb_set_field(tpb_handle h, int field, const double* data, int on_device) {
                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     TPB_CUDA(cudaStreamSynchronize(h->stream));
     h->fld_set[field] = true;
+    h->trans_dirty = true;
     TPB_CATCH(h)
 }
 
@@ -189,6 +194,7 @@ int tpb_set_field_ghost(tpb_handle h, int field, const double* lo, const double*
     if (lo) TPB_CUDA(cudaMemcpyAsync(h->fld_lo[field], lo, h->g.np * sizeof(double), kind, h->stream));
     if (hi) TPB_CUDA(cudaMemcpyAsync(h->fld_hi[field], hi, h->g.np * sizeof(double), kind, h->stream));
     TPB_CUDA(cudaStreamSynchronize(h->stream));
+    h->trans_dirty = true;
     TPB_CATCH(h)
 }
 
@@ -414,6 +420,7 @@ int tpb_exchange_static(tpb_handle h) {
     TPB_REQUIRE(h, TPB_ERR_ARG, "null handle");
     for (int f = 0; f < 5; f++)
         if (h->fld_set[f]) tpb_halo_vector(h, h->fld[f], 1, h->fld_lo[f], h->fld_hi[f]);
+    h->trans_dirty = true;
     TPB_CUDA(cudaStreamSynchronize(h->stream));
     TPB_CATCH(h)
 }

@@ -4,121 +4,28 @@
 //   singlephase.py:120-127 (2-D), :226-235 (3-D); twophase.py:162-178 (2-D), :333-354 (3-D)
 // and the source terms singlephase.py:151-165, twophase.py:388-411.
 //
-// One thread per cell, x fastest => every load/store of a field or of a Jacobian slot is a
-// fully coalesced 256 B row per warp.  The Jacobian is written in block-stencil layout
-// J[s][r][c][cell] (no column indices).  Facet fluxes are evaluated from the row cell's side
-// for each of its 4|6 faces (no atomics, no colouring); the derivative blocks come from
-// forward-mode duals over the 2*nf unknowns of the two cells sharing the face, so the
-// Jacobian is the exact derivative with the upwind conditionals frozen - what UFL's
-// derivative() gives the reference (thermalmodel.py:36).
+// Two launches per assembly:
+//   props_kernel     the transcendental part of the property laws (physicalparameters.py:37-90: two exp, one
+//                    pow per cell) evaluated ONCE per cell (owned + ghost planes) into a 16|40 B/cell scratch:
+//                    rho_o, rho_o/mu_o [, rho_w, d rho_w/dT, rho_w/mu_w]
+//   assemble_kernel  one thread per cell, x fastest => every load/store of a field or of a Jacobian slot is a
+//                    coalesced 256 B row per warp; the 4|6 facet fluxes of the cell are evaluated from the row
+//                    side (no atomics, no colouring) with hand-derived partials w.r.t. the 2*nf unknowns of
+//                    the two cells sharing the face, upwind conditionals frozen - the exact derivative UFL's
+//                    derivative() gives the reference (thermalmodel.py:36).  The Jacobian is written once, in
+//                    block-stencil layout J[s][r][c][cell] (no column indices), with streaming stores.
+// Compulsory traffic (3-D two-phase): 80 B in + 24 B F + 504 B J = 608 B/cell; the scratch adds 40 B written
+// and 40 B read (neighbour re-reads hit L1/L2).
+#include <stdlib.h>
+
 #include "tpb_internal.cuh"
 
 namespace {
-
-// per-cell quantities with partials w.r.t. the cell's own unknowns
-template <int NF>
-struct CellProps {
-    Dual<NF> p, T;
-    Dual<NF> S;        // two-phase only
-    Dual<NF> rho_o;    // oil density
-    Dual<NF> rho_w;    // two-phase only
-    Dual<NF> lam_o;    // k_ro rho_o / mu_o   (single-phase: rho_o / mu_o)
-    Dual<NF> lam_w;    // k_rw rho_w / mu_w
-    Dual<NF> kT;       // conductivity (constant partials for single-phase)
-};
-
-template <int NF>
-__device__ __forceinline__ CellProps<NF> cell_props(const DevParams& P, const double* u, double phi, double kT_static) {
-    CellProps<NF> c;
-    c.p = dvar<NF>(u[0], 0);
-    c.T = dvar<NF>(u[1], 1);
-    double ro, ro_p, ro_T, imo, imo_T;
-    oil_rho_d(P, u[0], u[1], ro, ro_p, ro_T);
-    oil_imu_d(P, u[1], imo, imo_T);
-    c.rho_o = dconst<NF>(ro);
-    c.rho_o.d[0] = ro_p;
-    c.rho_o.d[1] = ro_T;
-    Dual<NF> im_o = dconst<NF>(imo);
-    im_o.d[1] = imo_T;
-    if constexpr (NF == 3) {
-        c.S = dvar<NF>(u[2], 2);
-        double rw, rw_p, rw_T, imw, imw_T;
-        water_rho_d(u[0], u[1], rw, rw_p, rw_T);
-        water_imu_d(u[1], imw, imw_T);
-        c.rho_w = dconst<NF>(rw);
-        c.rho_w.d[0] = rw_p;
-        c.rho_w.d[1] = rw_T;
-        Dual<NF> im_w = dconst<NF>(imw);
-        im_w.d[1] = imw_T;
-        c.lam_o = c.S * c.rho_o * im_o;            // rel_perm_o = S_o  (physicalparameters.py:92-94)
-        c.lam_w = (1.0 - c.S) * c.rho_w * im_w;    // rel_perm_w = 1 - S_o (:96-98)
-        // kT = phi*(S ko + (1-S) kw) + (1-phi) kr   (twophase.py:135,311)
-        c.kT = phi * (P.ko * c.S + P.kw * (1.0 - c.S)) + (1.0 - phi) * P.kr;
-    } else {
-        c.S = dconst<NF>(0.0);
-        c.rho_w = dconst<NF>(0.0);
-        c.lam_w = dconst<NF>(0.0);
-        c.lam_o = c.rho_o * im_o;
-        c.kT = dconst<NF>(kT_static);
-    }
-    return c;
-}
-
-template <int NF, int OFF>
-__device__ __forceinline__ void embed_props(const CellProps<NF>& a, CellProps<2 * NF>& b) {
-    b.p = dembed<2 * NF, OFF, NF>(a.p);
-    b.T = dembed<2 * NF, OFF, NF>(a.T);
-    b.S = dembed<2 * NF, OFF, NF>(a.S);
-    b.rho_o = dembed<2 * NF, OFF, NF>(a.rho_o);
-    b.rho_w = dembed<2 * NF, OFF, NF>(a.rho_w);
-    b.lam_o = dembed<2 * NF, OFF, NF>(a.lam_o);
-    b.lam_w = dembed<2 * NF, OFF, NF>(a.lam_w);
-    b.kT = dembed<2 * NF, OFF, NF>(a.kT);
-}
 
 __device__ __forceinline__ double harm(double a, double b) {
     // conditional(gt(avg(K),0), K('+')*K('-')/avg(K), 0)   singlephase.py:98
     double s = 0.5 * (a + b);
     return s > 0.0 ? a * b / s : 0.0;
-}
-
-// Fluxes through one face; `pl` is the '+' cell (lower index), `mi` the '-' cell.
-// f[r] is added to the '+' row and subtracted from the '-' row (jump(test) = test+ - test-).
-// partial slots: [0, NF) = '+' unknowns, [NF, 2NF) = '-' unknowns.
-template <int NF>
-__device__ __forceinline__ void face_flux(const DevParams& P, const CellProps<2 * NF>& pl,
-                                          const CellProps<2 * NF>& mi, double Kf, double area, double ih, double grav,
-                                          Dual<2 * NF>* f) {
-    constexpr int NV = 2 * NF;
-    Dual<NV> dp = ih * (pl.p - mi.p);                    // jump(p)/Delta_h
-    Dual<NV> dT = ih * (pl.T - mi.T);
-    double aK = area * Kf;
-    if constexpr (NF == 2) {
-        // singlephase.py:215 z_flow = jump(p)/Delta_h - g*avg(rho_o); lateral: jump(p)/Delta_h
-        Dual<NV> fl = dp - (0.5 * grav) * (pl.rho_o + mi.rho_o);
-        bool up = fl.v > 0.0;
-        Dual<NV> lam = up ? pl.lam_o : mi.lam_o;
-        Dual<NV> Tup = up ? pl.T : mi.T;
-        Dual<NV> fm = aK * (lam * fl);                   // a_flow (:121,227-228)
-        Dual<NV> kTf = dconst<NV>(harm(pl.kT.v, mi.kT.v));
-        f[0] = fm;
-        f[1] = P.c_v_o * (Tup * fm) + area * (kTf * dT); // a_advec + a_diff (:124-125,231-233)
-    } else {
-        // twophase.py:317-318
-        Dual<NV> fl_w = dp - (0.5 * grav) * (pl.rho_w + mi.rho_w);
-        Dual<NV> fl_o = dp - (0.5 * grav) * (pl.rho_o + mi.rho_o);
-        bool upw = fl_w.v > 0.0, upo = fl_o.v > 0.0;
-        Dual<NV> fw = aK * ((upw ? pl.lam_w : mi.lam_w) * fl_w);   // :334-335
-        Dual<NV> fo = aK * ((upo ? pl.lam_o : mi.lam_o) * fl_o);   // :338-339
-        Dual<NV> few = P.c_v_w * ((upw ? pl.T : mi.T) * fw);       // :350-351
-        Dual<NV> feo = P.c_v_o * ((upo ? pl.T : mi.T) * fo);
-        // harmonic conductivity, state dependent (:315)
-        Dual<NV> ksum = 0.5 * (pl.kT + mi.kT);
-        Dual<NV> kTf = ksum.v > 0.0 ? (pl.kT * mi.kT) / ksum : dconst<NV>(0.0);
-        f[0] = P.Wp * (P.c_v_w * fw + P.c_v_o * fo);     // weighted-sum pressure equation (:343-346)
-        f[1] = few + feo + area * (kTf * dT);            // :352
-        f[2] = P.Wo * fo;
-    }
 }
 
 template <int NF>
@@ -127,164 +34,359 @@ struct Fields {
     GField phi, K[3], kT;
 };
 
-template <int NF>
 __device__ __forceinline__ double gl(const GField& f, long long c, long long n, int np) {
     return c < 0 ? f.lo[c + np] : (c >= n ? f.hi[c - n] : f.v[c]);
 }
 
-template <int NF, int DIM, bool JAC>
-__global__ void __launch_bounds__(128) assemble_kernel(Fields<NF> fl, const double* __restrict__ u_old, double idt,
-                                                       Geom g, DevParams P, double* __restrict__ F,
-                                                       double* __restrict__ J) {
+// scratch layout: q*(n + 2 np) + (np + cell), cell in [-np, n + np)
+//   q: 0 rho_o, 1 m_o = rho_o/mu_o, 2 d m_o/dT [, 3 rho_w, 4 d rho_w/dT, 5 m_w = rho_w/mu_w, 6 d m_w/dT]
+constexpr int NSCR1 = 3, NSCR2 = 7;
+
+template <int NF>
+__global__ void __launch_bounds__(256) props_kernel(Fields<NF> fl, long long n, int np, int has_lo, int has_hi,
+                                                    DevParams P, double* __restrict__ scr) {
+    const long long ne = n + 2LL * np;
+    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    long long c = e - np;
+    if ((c < 0 && !has_lo) || (c >= n && !has_hi)) return;
+    double p = gl(fl.u[0], c, n, np), T = gl(fl.u[1], c, n, np);
+    double ro, ro_p, ro_T, imo, imo_T;
+    oil_rho_d(P, p, T, ro, ro_p, ro_T);
+    oil_imu_d(P, T, imo, imo_T);
+    scr[e] = ro;
+    scr[ne + e] = ro * imo;
+    scr[2 * ne + e] = ro_T * imo + ro * imo_T;
+    if (NF == 3) {
+        double rw, rw_p, rw_T, imw, imw_T;
+        water_rho_d(p, T, rw, rw_p, rw_T);
+        water_imu_d(T, imw, imw_T);
+        scr[3 * ne + e] = rw;
+        scr[4 * ne + e] = rw_T;
+        scr[5 * ne + e] = rw * imw;
+        scr[6 * ne + e] = rw_T * imw + rw * imw_T;
+    }
+}
+
+// static face transmissibilities area * harmonic K of the face between a cell and its +axis neighbour
+// (K_facet of singlephase.py:98-101,207-211); 0 on the domain boundary.  tlo: the slab's bottom faces.
+template <int DIM>
+__global__ void __launch_bounds__(256) trans_kernel(GField Kx, GField Ky, GField Kz, Geom g, double* __restrict__ tx,
+                                                    double* __restrict__ ty, double* __restrict__ tz,
+                                                    double* __restrict__ tlo) {
+    const long long n = g.n;
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int nx = g.nx, ny = g.ny, np = g.np;
+    int i = (int)(c % nx);
+    long long t = c / nx;
+    int j = (int)(t % ny), k = (int)(t / ny);
+    tx[c] = i < nx - 1 ? g.area[0] * harm(Kx.v[c], Kx.v[c + 1]) : 0.0;
+    if (DIM == 2) {
+        bool ex = j < ny - 1 || g.has_hi;
+        ty[c] = ex ? g.area[1] * harm(Ky.v[c], gl(Ky, c + nx, n, np)) : 0.0;
+        if (j == 0 && g.has_lo) tlo[c] = g.area[1] * harm(Ky.lo[c], Ky.v[c]);
+    } else {
+        ty[c] = j < ny - 1 ? g.area[1] * harm(Ky.v[c], Ky.v[c + nx]) : 0.0;
+        bool ex = k < g.nz - 1 || g.has_hi;
+        tz[c] = ex ? g.area[2] * harm(Kz.v[c], gl(Kz, c + np, n, np)) : 0.0;
+        if (k == 0 && g.has_lo) tlo[c] = g.area[2] * harm(Kz.lo[c], Kz.v[c]);
+    }
+}
+
+// everything the flux through a face needs from one of its two cells
+template <int NF>
+struct Side {
+    double p, T, S;
+    double ro, mo, moT;
+    double rw, rwT, mw, mwT;
+    double kT, kT_S;
+};
+
+template <int NF, bool HALO>
+__device__ __forceinline__ Side<NF> load_side(const DevParams& P, const Fields<NF>& fl, const double* __restrict__ scr,
+                                              long long n, int np, long long ne, long long c) {
+    Side<NF> q;
+    const long long e = c + np;
+    q.p = HALO ? gl(fl.u[0], c, n, np) : fl.u[0].v[c];
+    q.T = HALO ? gl(fl.u[1], c, n, np) : fl.u[1].v[c];
+    q.ro = scr[e];
+    q.mo = scr[ne + e];
+    q.moT = scr[2 * ne + e];
+    if (NF == 3) {
+        q.S = HALO ? gl(fl.u[NF - 1], c, n, np) : fl.u[NF - 1].v[c];
+        q.rw = scr[3 * ne + e];
+        q.rwT = scr[4 * ne + e];
+        q.mw = scr[5 * ne + e];
+        q.mwT = scr[6 * ne + e];
+        const double phi = HALO ? gl(fl.phi, c, n, np) : fl.phi.v[c];
+        q.kT = phi * (P.ko * q.S + P.kw * (1.0 - q.S)) + (1.0 - phi) * P.kr;   // twophase.py:135,311
+        q.kT_S = phi * (P.ko - P.kw);
+    } else {
+        q.S = 1.0;
+        q.rw = q.rwT = q.mw = q.mwT = 0.0;
+        q.kT = HALO ? gl(fl.kT, c, n, np) : fl.kT.v[c];
+        q.kT_S = 0.0;
+    }
+    return q;
+}
+
+// Flux through one face; `pl` is the '+' cell (lower index), `mi` the '-' cell.  f[r] is added to the '+' row
+// and subtracted from the '-' row (jump(test) = test+ - test-).  dP[r][c] / dM[r][c] are the partials of f[r]
+// w.r.t. unknown c of the '+' / '-' cell.  aK = area * K_facet, Ak = area / Delta_h, gh = g/2 on horizontal facets.
+template <int NF, bool JAC>
+__device__ __forceinline__ void face_flux(const DevParams& P, const Side<NF>& pl, const Side<NF>& mi, double aK,
+                                          double Ak, double ih, double gh, double* f, double (*dP)[NF],
+                                          double (*dM)[NF]) {
+    constexpr double CO_P = 5.5e-4, CO_T = -2.5e-4, CW_P = 3.98854e-4;   // physicalparameters.py:41-46,77-82
+    const double dp = ih * (pl.p - mi.p);                       // jump(p)/Delta_h
+    const double dTj = pl.T - mi.T;
+    // ---- oil phase (the only phase of the single-phase model): singlephase.py:215, twophase.py:318
+    const double flo = dp - gh * (pl.ro + mi.ro);
+    const bool upo = flo > 0.0;
+    const Side<NF>& uo = upo ? pl : mi;
+    const double So = NF == 3 ? uo.S : 1.0;                     // rel_perm_o = S_o (:92-94)
+    const double lamo = So * uo.mo;
+    const double Tuo = uo.T;
+    const double Fo = aK * lamo * flo;                          // a_flow (:121,227-228 | :338-339)
+    double Fo_P[3], Fo_M[3];
+    if (JAC) {
+        // partials of the upwinded mobility w.r.t. the upwind cell's (p, T, S)
+        const double a_p = aK * flo * CO_P * lamo, a_T = aK * flo * So * uo.moT, a_S = aK * flo * uo.mo;
+        const double al = aK * lamo;
+        Fo_P[0] = al * (ih - gh * CO_P * pl.ro) + (upo ? a_p : 0.0);
+        Fo_P[1] = al * (-gh * CO_T * pl.ro) + (upo ? a_T : 0.0);
+        Fo_P[2] = upo ? a_S : 0.0;
+        Fo_M[0] = al * (-ih - gh * CO_P * mi.ro) + (upo ? 0.0 : a_p);
+        Fo_M[1] = al * (-gh * CO_T * mi.ro) + (upo ? 0.0 : a_T);
+        Fo_M[2] = upo ? 0.0 : a_S;
+    }
+    if (NF == 2) {
+        const double kTf = harm(pl.kT, mi.kT);
+        const double ce = P.c_v_o * Tuo;
+        f[0] = Fo;
+        f[1] = ce * Fo + Ak * kTf * dTj;                        // a_advec + a_diff (:124-125,231-233)
+        if (JAC) {
+#pragma unroll
+            for (int c = 0; c < NF; c++) {
+                dP[0][c] = Fo_P[c];
+                dM[0][c] = Fo_M[c];
+                dP[1][c] = ce * Fo_P[c];
+                dM[1][c] = ce * Fo_M[c];
+            }
+            dP[1][1] += (upo ? P.c_v_o * Fo : 0.0) + Ak * kTf;
+            dM[1][1] += (upo ? 0.0 : P.c_v_o * Fo) - Ak * kTf;
+        }
+    } else {
+        // ---- water phase: twophase.py:317,334-335
+        const double flw = dp - gh * (pl.rw + mi.rw);
+        const bool upw = flw > 0.0;
+        const Side<NF>& uw = upw ? pl : mi;
+        const double Sw = 1.0 - uw.S;                           // rel_perm_w = 1 - S_o (:96-98)
+        const double lamw = Sw * uw.mw;
+        const double Tuw = uw.T;
+        const double Fw = aK * lamw * flw;
+        // harmonic conductivity, state dependent (:315)
+        const double ks = 0.5 * (pl.kT + mi.kT);
+        const double iks = ks > 0.0 ? 1.0 / ks : 0.0;
+        const double kTf = pl.kT * mi.kT * iks;
+        const double cew = P.c_v_w * Tuw, ceo = P.c_v_o * Tuo;
+        f[0] = P.Wp * (P.c_v_w * Fw + P.c_v_o * Fo);           // weighted-sum pressure equation (:343-346)
+        f[1] = cew * Fw + ceo * Fo + Ak * kTf * dTj;            // :350-352
+        f[2] = P.Wo * Fo;
+        if (JAC) {
+            double Fw_P[3], Fw_M[3];
+            const double b_p = aK * flw * CW_P * lamw, b_T = aK * flw * Sw * uw.mwT, b_S = -aK * flw * uw.mw;
+            const double bl = aK * lamw;
+            Fw_P[0] = bl * (ih - gh * CW_P * pl.rw) + (upw ? b_p : 0.0);
+            Fw_P[1] = bl * (-gh * pl.rwT) + (upw ? b_T : 0.0);
+            Fw_P[2] = upw ? b_S : 0.0;
+            Fw_M[0] = bl * (-ih - gh * CW_P * mi.rw) + (upw ? 0.0 : b_p);
+            Fw_M[1] = bl * (-gh * mi.rwT) + (upw ? 0.0 : b_T);
+            Fw_M[2] = upw ? 0.0 : b_S;
+            const double wpw = P.Wp * P.c_v_w, wpo = P.Wp * P.c_v_o;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                dP[0][c] = wpw * Fw_P[c] + wpo * Fo_P[c];
+                dM[0][c] = wpw * Fw_M[c] + wpo * Fo_M[c];
+                dP[1][c] = cew * Fw_P[c] + ceo * Fo_P[c];
+                dM[1][c] = cew * Fw_M[c] + ceo * Fo_M[c];
+                dP[2][c] = P.Wo * Fo_P[c];
+                dM[2][c] = P.Wo * Fo_M[c];
+            }
+            const double adv = P.c_v_w * Fw, ado = P.c_v_o * Fo, cond = Ak * kTf;
+            dP[1][1] += (upw ? adv : 0.0) + (upo ? ado : 0.0) + cond;
+            dM[1][1] += (upw ? 0.0 : adv) + (upo ? 0.0 : ado) - cond;
+            // d kTf / d k+ = k-^2 / (2 ks^2), and symmetrically
+            const double hk = 0.5 * iks * iks * Ak * dTj;
+            dP[1][2] += hk * mi.kT * mi.kT * pl.kT_S;
+            dM[1][2] += hk * pl.kT * pl.kT * mi.kT_S;
+        }
+    }
+}
+
+struct Trans {
+    const double* t[3];
+    const double* lo;
+};
+
+template <int NF, int DIM, bool JAC, bool HALO, int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, const double* __restrict__ u_old,
+                                                             const double* __restrict__ scr, Trans tr, double idt,
+                                                             Geom g, DevParams P, double* __restrict__ F,
+                                                             double* __restrict__ J) {
     const long long n = g.n;
     long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n) return;
     const int nx = g.nx, ny = g.ny, np = g.np;
+    const long long ne = n + 2LL * np;
     int i = (int)(cell % nx);
     long long t = cell / nx;
     int j = (int)(t % ny);
     int k = (int)(t / ny);
 
-    double uc[NF];
-#pragma unroll
-    for (int f = 0; f < NF; f++) uc[f] = fl.u[f].v[cell];
-    double phi = fl.phi.v[cell];
-    double kTs = (NF == 2) ? fl.kT.v[cell] : 0.0;
-    CellProps<NF> me = cell_props<NF>(P, uc, phi, kTs);
+    const Side<NF> me = load_side<NF, false>(P, fl, scr, n, np, ne, cell);
+    const double phi = fl.phi.v[cell];
 
     double R[NF];
     double D[NF][NF];
-#pragma unroll
-    for (int r = 0; r < NF; r++) {
-        R[r] = 0.0;
-#pragma unroll
-        for (int c = 0; c < NF; c++) D[r][c] = 0.0;
-    }
 
     // ---- accumulation (cell integrals) ------------------------------------------------------
     {
-        double po = u_old[cell], To = u_old[n + cell];
-        double w = g.vol * idt;
-        if constexpr (NF == 2) {
-            double ro_old = oil_rho_v(P, po, To);
-            Dual<NF> am = (w * phi) * (me.rho_o - ro_old);                       // singlephase.py:120
-            Dual<NF> ae = (w * phi * P.c_v_o) * (me.rho_o * me.T - ro_old * To)  // :123
-                          + (w * (1.0 - phi) * P.rho_r * P.c_r) * (me.T - To);
-            R[0] += am.v;
-            R[1] += ae.v;
-#pragma unroll
-            for (int c = 0; c < NF; c++) {
-                D[0][c] += am.d[c];
-                D[1][c] += ae.d[c];
+        constexpr double CO_P = 5.5e-4, CO_T = -2.5e-4, CW_P = 3.98854e-4;
+        const double po = u_old[cell], To = u_old[n + cell];
+        const double w = g.vol * idt;
+        const double ro_old = oil_rho_v(P, po, To);
+        const double rk = w * (1.0 - phi) * P.rho_r * P.c_r;
+        const double wp = w * phi;
+        if (NF == 2) {
+            R[0] = wp * (me.ro - ro_old);                                              // singlephase.py:120
+            R[1] = wp * P.c_v_o * (me.ro * me.T - ro_old * To) + rk * (me.T - To);      // :123
+            if (JAC) {
+                D[0][0] = wp * CO_P * me.ro;
+                D[0][1] = wp * CO_T * me.ro;
+                D[1][0] = wp * P.c_v_o * CO_P * me.ro * me.T;
+                D[1][1] = wp * P.c_v_o * (CO_T * me.ro * me.T + me.ro) + rk;
             }
         } else {
-            double So = u_old[2 * n + cell];
-            double ro_old = oil_rho_v(P, po, To), rw_old = water_rho_v(po, To);
-            Dual<NF> Sw = 1.0 - me.S;
-            Dual<NF> aw = (w * phi) * (me.rho_w * Sw - rw_old * (1.0 - So));     // twophase.py:333
-            Dual<NF> ao = (w * phi) * (me.rho_o * me.S - ro_old * So);          // :337
-            Dual<NF> ae = (w * phi * P.c_v_w) * (me.rho_w * Sw * me.T - rw_old * (1.0 - So) * To) +
-                          (w * phi * P.c_v_o) * (me.rho_o * me.S * me.T - ro_old * So * To) +
-                          (w * (1.0 - phi) * P.rho_r * P.c_r) * (me.T - To);    // :349
-            Dual<NF> ap = P.Wp * (P.c_v_w * aw + P.c_v_o * ao);                 // :344
-            Dual<NF> as = P.Wo * ao;
-            R[0] += ap.v;
-            R[1] += ae.v;
-            R[2] += as.v;
-#pragma unroll
-            for (int c = 0; c < NF; c++) {
-                D[0][c] += ap.d[c];
-                D[1][c] += ae.d[c];
-                D[2][c] += as.d[c];
+            const double So = u_old[2 * n + cell];
+            const double rw_old = water_rho_v(po, To);
+            const double S = me.S, Sw = 1.0 - me.S, T = me.T;
+            const double aw = wp * (me.rw * Sw - rw_old * (1.0 - So));                  // twophase.py:333
+            const double ao = wp * (me.ro * S - ro_old * So);                           // :337
+            R[0] = P.Wp * (P.c_v_w * aw + P.c_v_o * ao);                                // :344
+            R[1] = wp * P.c_v_w * (me.rw * Sw * T - rw_old * (1.0 - So) * To) +
+                   wp * P.c_v_o * (me.ro * S * T - ro_old * So * To) + rk * (T - To);   // :349
+            R[NF - 1] = P.Wo * ao;
+            if (JAC) {
+                const double aw_p = wp * CW_P * me.rw * Sw, aw_T = wp * me.rwT * Sw, aw_S = -wp * me.rw;
+                const double ao_p = wp * CO_P * me.ro * S, ao_T = wp * CO_T * me.ro * S, ao_S = wp * me.ro;
+                const double h_p = P.c_v_w * aw_p + P.c_v_o * ao_p, h_T = P.c_v_w * aw_T + P.c_v_o * ao_T,
+                             h_S = P.c_v_w * aw_S + P.c_v_o * ao_S;
+                D[0][0] = P.Wp * h_p;
+                D[0][1] = P.Wp * h_T;
+                D[0][NF - 1] = P.Wp * h_S;
+                D[1][0] = h_p * T;
+                D[1][1] = h_T * T + wp * (P.c_v_w * me.rw * Sw + P.c_v_o * me.ro * S) + rk;
+                D[1][NF - 1] = h_S * T;
+                D[NF - 1][0] = P.Wo * ao_p;
+                D[NF - 1][1] = P.Wo * ao_T;
+                D[NF - 1][NF - 1] = P.Wo * ao_S;
             }
         }
     }
 
     // ---- facet integrals ------------------------------------------------------------------------
-    constexpr int NV = 2 * NF;
-    CellProps<NV> me_pl, me_mi;
-    embed_props<NF, 0>(me, me_pl);
-    embed_props<NF, NF>(me, me_mi);
-
 #pragma unroll
     for (int s = 1; s < 2 * DIM + 1; s++) {
         const int axis = (s - 1) >> 1;
         const bool hi_side = ((s - 1) & 1) != 0;   // neighbour has the higher index => this cell is '+'
         bool exists;
         long long nb;
+        double aK;                                 // area * K_facet
         if (axis == 0) {
             exists = hi_side ? (i < nx - 1) : (i > 0);
             nb = cell + (hi_side ? 1 : -1);
+            aK = exists ? tr.t[0][hi_side ? cell : nb] : 0.0;
         } else if (axis == 1) {
-            if (DIM == 2)
+            if (DIM == 2) {
                 exists = hi_side ? (j < ny - 1 || g.has_hi) : (j > 0 || g.has_lo);
-            else
+                nb = cell + (hi_side ? nx : -nx);
+                aK = !exists ? 0.0 : (hi_side ? tr.t[1][cell] : (nb >= 0 ? tr.t[1][nb] : tr.lo[cell]));
+            } else {
                 exists = hi_side ? (j < ny - 1) : (j > 0);
-            nb = cell + (hi_side ? nx : -nx);
+                nb = cell + (hi_side ? nx : -nx);
+                aK = exists ? tr.t[1][hi_side ? cell : nb] : 0.0;
+            }
         } else {
             exists = hi_side ? (k < g.nz - 1 || g.has_hi) : (k > 0 || g.has_lo);
-            nb = cell + (hi_side ? (long long)nx * ny : -(long long)nx * ny);
+            nb = cell + (hi_side ? (long long)np : -(long long)np);
+            aK = !exists ? 0.0 : (hi_side ? tr.t[2][cell] : (nb >= 0 ? tr.t[2][nb] : tr.lo[cell]));
         }
-        double Oblk[NF][NF];
+        double O[NF][NF];
 #pragma unroll
         for (int r = 0; r < NF; r++)
 #pragma unroll
-            for (int c = 0; c < NF; c++) Oblk[r][c] = 0.0;
+            for (int c = 0; c < NF; c++) O[r][c] = 0.0;
 
         if (exists) {
-            double un[NF];
-#pragma unroll
-            for (int f = 0; f < NF; f++) un[f] = gl<NF>(fl.u[f], nb, n, np);
-            double phin = gl<NF>(fl.phi, nb, n, np);
-            double kTn = (NF == 2) ? gl<NF>(fl.kT, nb, n, np) : 0.0;
-            double Kn = gl<NF>(fl.K[axis], nb, n, np);
-            double Kf = harm(fl.K[axis].v[cell], Kn);
-            CellProps<NF> other = cell_props<NF>(P, un, phin, kTn);
-            double grav = (axis == 2) ? P.g : 0.0;
-            Dual<NV> f[NF];
+            const bool slab_axis = (axis == DIM - 1);
+            const Side<NF> ot = (HALO && slab_axis) ? load_side<NF, true>(P, fl, scr, n, np, ne, nb)
+                                                    : load_side<NF, false>(P, fl, scr, n, np, ne, nb);
+            const double gh = (axis == 2) ? 0.5 * P.g : 0.0;
+            const double ih = g.ih[axis], Ak = g.area[axis] * ih;
+            double f[NF], dP[NF][NF], dM[NF][NF];
             if (hi_side) {
-                CellProps<NV> ot;
-                embed_props<NF, NF>(other, ot);
-                face_flux<NF>(P, me_pl, ot, Kf, g.area[axis], 1.0 / g.h[axis], grav, f);
+                face_flux<NF, JAC>(P, me, ot, aK, Ak, ih, gh, f, dP, dM);
 #pragma unroll
                 for (int r = 0; r < NF; r++) {
-                    R[r] += f[r].v;
+                    R[r] += f[r];
+                    if (JAC) {
 #pragma unroll
-                    for (int c = 0; c < NF; c++) {
-                        D[r][c] += f[r].d[c];
-                        Oblk[r][c] = f[r].d[NF + c];
+                        for (int c = 0; c < NF; c++) {
+                            D[r][c] += dP[r][c];
+                            O[r][c] = dM[r][c];
+                        }
                     }
                 }
             } else {
-                CellProps<NV> ot;
-                embed_props<NF, 0>(other, ot);
-                face_flux<NF>(P, ot, me_mi, Kf, g.area[axis], 1.0 / g.h[axis], grav, f);
+                face_flux<NF, JAC>(P, ot, me, aK, Ak, ih, gh, f, dP, dM);
 #pragma unroll
                 for (int r = 0; r < NF; r++) {
-                    R[r] -= f[r].v;
+                    R[r] -= f[r];
+                    if (JAC) {
 #pragma unroll
-                    for (int c = 0; c < NF; c++) {
-                        D[r][c] -= f[r].d[NF + c];
-                        Oblk[r][c] = -f[r].d[c];
+                        for (int c = 0; c < NF; c++) {
+                            D[r][c] -= dM[r][c];
+                            O[r][c] = -dP[r][c];
+                        }
                     }
                 }
             }
         }
         if (JAC) {
+            double* jp = J + (long long)(s * NF * NF) * n + cell;
 #pragma unroll
             for (int r = 0; r < NF; r++)
 #pragma unroll
-                for (int c = 0; c < NF; c++) J[((long long)(s * NF + r) * NF + c) * n + cell] = Oblk[r][c];
+                for (int c = 0; c < NF; c++) {
+                    __stcs(jp, O[r][c]);
+                    jp += n;
+                }
         }
     }
 
 #pragma unroll
     for (int r = 0; r < NF; r++) F[(long long)r * n + cell] = R[r];
     if (JAC) {
+        double* jp = J + cell;
 #pragma unroll
         for (int r = 0; r < NF; r++)
 #pragma unroll
-            for (int c = 0; c < NF; c++) J[((long long)r * NF + c) * n + cell] = D[r][c];
+            for (int c = 0; c < NF; c++) {
+                *jp = D[r][c];
+                jp += n;
+            }
     }
 }
 
@@ -411,6 +513,34 @@ __global__ void sources_kernel(int ncells, const int64_t* __restrict__ cells, co
     }
 }
 
+template <int NF, int DIM, bool HALO>
+void launch_k(tpb_handle_s* h, const Fields<NF>& fl, const double* u_old, double dt, double* F, double* J) {
+    const long long n = h->g.n;
+    Trans tr;
+    tr.t[0] = h->trans[0];
+    tr.t[1] = h->trans[1];
+    tr.t[2] = h->trans[2];
+    tr.lo = h->trans_lo;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    static int variant = getenv("TPB_ASM_MINB") ? atoi(getenv("TPB_ASM_MINB")) : 4;
+#define TPB_ASM(JAC, MINB) \
+    assemble_kernel<NF, DIM, JAC, HALO, MINB><<<blocks, threads, 0, h->stream>>>(fl, u_old, h->scr, tr, 1.0 / dt, h->g, h->dp, F, J)
+    if (J) {
+        if (variant == 3)
+            TPB_ASM(true, 3);
+        else if (variant == 5)
+            TPB_ASM(true, 5);
+        else if (variant == 6)
+            TPB_ASM(true, 6);
+        else
+            TPB_ASM(true, 4);
+    } else {
+        TPB_ASM(false, 6);
+    }
+#undef TPB_ASM
+}
+
 template <int NF, int DIM>
 void launch_t(tpb_handle_s* h, const double* u, const double* u_old, double dt, double* F, double* J) {
     Fields<NF> fl;
@@ -433,12 +563,24 @@ void launch_t(tpb_handle_s* h, const double* u, const double* u_old, double dt, 
     fl.K[1] = gf(TPB_KY);
     fl.K[2] = gf(DIM == 3 ? TPB_KZ : TPB_KY);
     fl.kT = gf(TPB_KT);
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    if (J)
-        assemble_kernel<NF, DIM, true><<<blocks, threads, 0, h->stream>>>(fl, u_old, 1.0 / dt, h->g, h->dp, F, J);
+    const long long ne = n + 2LL * np;
+    if (!h->scr) h->scr = tpb_dalloc<double>((size_t)(NF == 3 ? NSCR2 : NSCR1) * ne);
+    if (h->trans_dirty) {
+        for (int a = 0; a < 3; a++)
+            if (!h->trans[a]) h->trans[a] = tpb_dalloc<double>(n);
+        if (!h->trans_lo) h->trans_lo = tpb_dalloc<double>(np);
+        trans_kernel<DIM><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(fl.K[0], fl.K[1], fl.K[2], h->g, h->trans[0],
+                                                                          h->trans[1], h->trans[2], h->trans_lo);
+        h->launches++;
+        h->trans_dirty = false;
+    }
+    props_kernel<NF><<<(unsigned)((ne + 255) / 256), 256, 0, h->stream>>>(fl, n, np, h->g.has_lo, h->g.has_hi, h->dp,
+                                                                         h->scr);
+    h->launches++;
+    if (h->g.has_lo || h->g.has_hi)
+        launch_k<NF, DIM, true>(h, fl, u_old, dt, F, J);
     else
-        assemble_kernel<NF, DIM, false><<<blocks, threads, 0, h->stream>>>(fl, u_old, 1.0 / dt, h->g, h->dp, F, J);
+        launch_k<NF, DIM, false>(h, fl, u_old, dt, F, J);
     h->launches++;
     if (h->nsrc_cells > 0) {
         const unsigned sb = (unsigned)((h->nsrc_cells + 127) / 128);

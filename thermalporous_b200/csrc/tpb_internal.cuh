@@ -37,6 +37,7 @@ struct Geom {
     int has_lo, has_hi;
     long long n;     // owned cells
     double h[3];     // centre distances Dx, Dy, Dz
+    double ih[3];    // 1 / h
     double area[3];  // facet measure per axis
     double vol;
 };
@@ -247,6 +248,12 @@ struct tpb_handle_s {
     // state ghost planes (nf * np each)
     double* u_lo = nullptr;
     double* u_hi = nullptr;
+    // per-cell property scratch of the assembly (owned + ghost planes), tpb_assemble.cu
+    double* scr = nullptr;
+    // static face transmissibilities area*K_facet per axis (+ the slab's bottom faces), rebuilt when a field changes
+    double* trans[3] = {nullptr, nullptr, nullptr};
+    double* trans_lo = nullptr;
+    bool trans_dirty = true;
     // generic vector ghost planes for SpMV inputs (nf * np each)
     double* x_lo = nullptr;
     double* x_hi = nullptr;
