@@ -195,16 +195,14 @@ def run_b200(args):
     prm = make_params()
     refine = world
     geo = make_geo(prm, NZ, refine)                 # global grid 60 x 220 x 85*world, Dz/world
-    nz_loc = geo.Nz // world
-    k0 = rank * nz_loc
-    sl = slice(k0 * geo.Nx * geo.Ny, (k0 + nz_loc) * geo.Nx * geo.Ny)
+    from thermalporous_b200.partition import Slab
+    slab = Slab(geo, world, rank)
     case = CS.WellCase(prm, geo, well_case="default")
-    ent_all = CS.source_entries(case, prm, geo)
-    ent = [(c - sl.start,) + tuple(r) for (c, *r) in ent_all if sl.start <= c < sl.stop]
-    eng = Engine(3, geo.Nx, geo.Ny, nz_loc, geo.Dx, geo.Dy, geo.Dz, 2, prm, device=local,
-                 has_lo=rank > 0, has_hi=rank < world - 1)
+    ent = slab.localize_sources(CS.source_entries(case, prm, geo))
+    nxl, nyl, nzl = slab.local_dims()
+    eng = Engine(3, nxl, nyl, nzl, geo.Dx, geo.Dy, geo.Dz, 2, prm, device=local, has_lo=slab.has_lo, has_hi=slab.has_hi)
     for fid, arr in ((L.TPB_PHI, geo.phi), (L.TPB_KX, geo.K_x), (L.TPB_KY, geo.K_y), (L.TPB_KZ, geo.K_z)):
-        eng.set_field(fid, arr[sl])
+        eng.set_field(fid, slab.take(arr))
     eng.set_sources(ent)
     if world > 1:
         uid = [eng.unique_id() if rank == 0 else None]
@@ -214,7 +212,7 @@ def run_b200(args):
     opts, _, desc = O.resolve(PC, 2)
     eng.set_solver_opts(**opts)
     n_loc = eng.n
-    n_glob = n_loc * world
+    n_glob = geo.ncell
     u = eng.tensor(np.stack([np.full(n_loc, prm.p_ref), np.full(n_loc, prm.T_prod), np.full(n_loc, prm.S_o)]))
     uo = u.clone()
     kw = dict(end=1e9, maxdt=MAXDT, small_dt_start=True, dt_init_fact=DT_INIT_FACT, two_phase=True, i_S=2, spe10=True)
