@@ -210,6 +210,10 @@ def run_b200(args):
         eng.comm_init(uid[0], rank, world)
         eng.exchange_static()
     opts, _, desc = O.resolve(PC, 2)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        opts[k] = float(v) if ("." in v or "e" in v) else int(v)
+        desc += " %s" % kv
     eng.set_solver_opts(**opts)
     n_loc = eng.n
     n_glob = geo.ncell
@@ -315,6 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], help="solver option override key=value (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,6 +16,7 @@
 //       triangular solves are two fully parallel colour sweeps.
 // PCCOMPOSITE multiplicative: y = B1 x ; y += B2 (x - J y).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -28,6 +29,7 @@ constexpr int MAXLEV = 40;
 struct MgLevel {
     int nx = 0, ny = 0, nz = 0;
     long long n = 0;
+    long long cap = 0;    // allocated cells (levels are re-shaped in place while they fit)
     int cx = 1, cy = 1, cz = 1;
     double* a = nullptr;  // ns * n
     bool own_a = false;
@@ -53,6 +55,11 @@ struct PcState {
     double *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
     double* strength = nullptr;  // 3 doubles (device)
     bool ready = false;
+    // the whole PC apply (~100 small dependent kernels) replayed as one CUDA graph on fixed in/out buffers
+    cudaGraphExec_t gexec = nullptr;
+    double *gx = nullptr, *gy = nullptr;
+    int64_t graph_nodes = 0;
+    bool graph_ok = false;
 };
 
 namespace {
@@ -342,9 +349,25 @@ __global__ void convdiff_sources_kernel(int ncells, const int64_t* __restrict__ 
 
 // ---- K7 multigrid kernels ---------------------------------------------------------------------
 struct LevGeom {
-    int nx, ny, nz, cx, cy, cz;
+    int nx, ny, nz, cx, cy, cz;   // cx,cy,cz in {1,2}: aggregate index = fine index >> (c - 1)
     long long n;
 };
+
+// clamped neighbour for branch-free stencil sweeps: index of the neighbour through slot s, or the cell itself
+// when the neighbour is outside (the caller discards that product with a select, so loads stay unconditional
+// and all of a thread's loads can be in flight together)
+__device__ __forceinline__ long long nbr_clamped(int nx, int ny, int nz, int i, int j, int k, long long c, int s,
+                                                 bool& exists) {
+    switch (s) {
+        case 1: exists = i > 0; return exists ? c - 1 : c;
+        case 2: exists = i < nx - 1; return exists ? c + 1 : c;
+        case 3: exists = j > 0; return exists ? c - nx : c;
+        case 4: exists = j < ny - 1; return exists ? c + nx : c;
+        case 5: exists = k > 0; return exists ? c - (long long)nx * ny : c;
+        case 6: exists = k < nz - 1; return exists ? c + (long long)nx * ny : c;
+        default: exists = true; return c;
+    }
+}
 
 // sum over cells of |a[2ax+1]| + |a[2ax+2]| for the three axes -> out[0..2] (atomics; a few thousand adds)
 template <int NS>
@@ -409,25 +432,42 @@ __global__ void __launch_bounds__(128) coarsen_op_kernel(const double* __restric
 
 // one colour of a red-black Gauss-Seidel sweep: colour = (i+j+k)&1.  Threads walk the cells of the
 // colour only (i = 2*ih + parity of the row).  zero_guess: x == 0 on entry, no neighbour reads.
-template <int NS>
+// PROLONG: the coarse correction is folded into this pass - a Gauss-Seidel update never reads the cell's own
+// old value, so after a correction x += omega P xc only the OTHER colour's corrected values matter, and they
+// are formed on the fly as x[nb] + omega xc[aggregate(nb)] (saves the prolongation pass over x entirely).
+template <int NS, bool PROLONG>
 __device__ __forceinline__ void rbgs_cell(const double* __restrict__ a, const double* __restrict__ b, double* x,
-                                          const LevGeom& g, int i, int j, int k, bool zero_guess) {
+                                          const LevGeom& g, int i, int j, int k, bool zero_guess,
+                                          const double* __restrict__ xc, int cnx, int cny, double omega) {
     long long c = i + (long long)g.nx * (j + (long long)g.ny * k);
     double acc = b[c];
     if (!zero_guess) {
+        double t[NS];
 #pragma unroll
         for (int s = 1; s < NS; s++) {
-            long long nb = nbr_cell(g.nx, g.ny, g.nz, i, j, k, c, s);
-            if (nb >= 0) acc -= a[(long long)s * g.n + c] * x[nb];
+            bool ex;
+            long long nb = nbr_clamped(g.nx, g.ny, g.nz, i, j, k, c, s, ex);
+            double xv = x[nb];
+            if (PROLONG) {
+                const int axis = (s - 1) >> 1, d = ((s - 1) & 1) ? 1 : -1;
+                const int ii = ex ? i + (axis == 0 ? d : 0) : i, jj = ex ? j + (axis == 1 ? d : 0) : j,
+                          kk = ex ? k + (axis == 2 ? d : 0) : k;
+                xv += omega * xc[(ii >> (g.cx - 1)) + (long long)cnx * ((jj >> (g.cy - 1)) + (long long)cny * (kk >> (g.cz - 1)))];
+            }
+            double p = a[(long long)s * g.n + c] * xv;
+            t[s] = ex ? p : 0.0;
         }
+#pragma unroll
+        for (int s = 1; s < NS; s++) acc -= t[s];
     }
-    double d = a[c];
-    x[c] = d != 0.0 ? acc / d : 0.0;
+    double d0 = a[c];
+    x[c] = d0 != 0.0 ? acc / d0 : 0.0;
 }
 
-template <int NS>
+template <int NS, bool PROLONG>
 __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a, const double* __restrict__ b,
-                                                   double* x, LevGeom g, int col, int zero_guess) {
+                                                   double* x, LevGeom g, int col, int zero_guess,
+                                                   const double* __restrict__ xc, int cnx, int cny, double omega) {
     const int nxh = (g.nx + 1) >> 1;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long rows = (long long)g.ny * g.nz;
@@ -437,28 +477,39 @@ __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a,
     int j = (int)(row % g.ny), k = (int)(row / g.ny);
     int i = 2 * ih + ((col + j + k) & 1);
     if (i >= g.nx) return;
-    rbgs_cell<NS>(a, b, x, g, i, j, k, zero_guess != 0);
+    rbgs_cell<NS, PROLONG>(a, b, x, g, i, j, k, zero_guess != 0, xc, cnx, cny, omega);
 }
 
-// bc[C] = sum over the aggregate of (b - A x)  (residual + restriction fused)
+// bc[C] = sum over the aggregate of (b - A x)  (residual + restriction fused).  The aggregate is walked as a
+// fully unrolled 2x2x2 box with predication so that the loads of all its fine cells are in flight together;
+// the summation order (k, j, i; within a cell diag, x-, x+, ...) is the one the CPU restatement uses.
 template <int NS>
 __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, const double* __restrict__ b,
                                                 const double* __restrict__ x, const LevGeom& f, int I, int Jc, int Kc) {
-    double sum = 0.0;
-    for (int dk = 0; dk < f.cz; dk++)
-        for (int dj = 0; dj < f.cy; dj++)
-            for (int di = 0; di < f.cx; di++) {
-                int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
-                if (i >= f.nx || j >= f.ny || k >= f.nz) continue;
-                long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
-                double acc = b[c] - a[c] * x[c];
+    double r[8];
 #pragma unroll
-                for (int s = 1; s < NS; s++) {
-                    long long nb = nbr_cell(f.nx, f.ny, f.nz, i, j, k, c, s);
-                    if (nb >= 0) acc -= a[(long long)s * f.n + c] * x[nb];
-                }
-                sum += acc;
-            }
+    for (int q = 0; q < 8; q++) {
+        const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
+        int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
+        const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz;
+        // an absent member of the aggregate is evaluated at the aggregate's first cell and discarded
+        i = ok ? i : I * f.cx;
+        j = ok ? j : Jc * f.cy;
+        k = ok ? k : Kc * f.cz;
+        long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
+        double acc = b[c] - a[c] * x[c];
+#pragma unroll
+        for (int s = 1; s < NS; s++) {
+            bool ex;
+            long long nb = nbr_clamped(f.nx, f.ny, f.nz, i, j, k, c, s, ex);
+            double p = a[(long long)s * f.n + c] * x[nb];
+            acc -= ex ? p : 0.0;
+        }
+        r[q] = ok ? acc : 0.0;
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) sum += r[q];
     return sum;
 }
 
@@ -480,7 +531,7 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(const double* __restri
     int i = (int)(c % f.nx);
     long long t = c / f.nx;
     int j = (int)(t % f.ny), k = (int)(t / f.ny);
-    long long C = (i / f.cx) + (long long)cg.nx * ((j / f.cy) + (long long)cg.ny * (k / f.cz));
+    long long C = (i >> (f.cx - 1)) + (long long)cg.nx * ((j >> (f.cy - 1)) + (long long)cg.ny * (k >> (f.cz - 1)));
     x[c] += omega * xc[C];
 }
 
@@ -518,8 +569,8 @@ struct TailArgs {
     double omega;
 };
 
-template <int NS>
-__device__ void tail_rbgs(const TailLevel& L, bool zero_guess) {
+template <int NS, bool PROLONG>
+__device__ void tail_rbgs(const TailLevel& L, bool zero_guess, const double* xc, int cnx, int cny, double omega) {
     const LevGeom& g = L.g;
     const int nxh = (g.nx + 1) >> 1;
     const long long total = (long long)g.ny * g.nz * nxh;
@@ -529,7 +580,12 @@ __device__ void tail_rbgs(const TailLevel& L, bool zero_guess) {
             long long row = t / nxh;
             int j = (int)(row % g.ny), k = (int)(row / g.ny);
             int i = 2 * ih + ((col + j + k) & 1);
-            if (i < g.nx) rbgs_cell<NS>(L.a, L.b, L.x, g, i, j, k, zero_guess && col == 0);
+            if (i < g.nx) {
+                if (PROLONG && col == 0)
+                    rbgs_cell<NS, true>(L.a, L.b, L.x, g, i, j, k, false, xc, cnx, cny, omega);
+                else
+                    rbgs_cell<NS, false>(L.a, L.b, L.x, g, i, j, k, zero_guess && col == 0, nullptr, 0, 0, 0.0);
+            }
         }
         __syncthreads();
     }
@@ -540,7 +596,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
     // down
     for (int l = 0; l < A.nlev - 1; l++) {
         const TailLevel& L = A.lev[l];
-        for (int s = 0; s < A.pre; s++) tail_rbgs<NS>(L, s == 0);
+        for (int s = 0; s < A.pre; s++) tail_rbgs<NS, false>(L, s == 0, nullptr, 0, 0, 0.0);
         const TailLevel& Cc = A.lev[l + 1];
         for (long long C = threadIdx.x; C < Cc.g.n; C += blockDim.x) {
             int I = (int)(C % Cc.g.nx);
@@ -552,22 +608,27 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
     // coarsest
     {
         const TailLevel& L = A.lev[A.nlev - 1];
-        for (int s = 0; s < A.coarse_sweeps; s++) tail_rbgs<NS>(L, s == 0);
+        for (int s = 0; s < A.coarse_sweeps; s++) tail_rbgs<NS, false>(L, s == 0, nullptr, 0, 0, 0.0);
     }
     // up
     for (int l = A.nlev - 2; l >= 0; l--) {
         const TailLevel& L = A.lev[l];
         const TailLevel& Cc = A.lev[l + 1];
         const LevGeom& f = L.g;
-        for (long long c = threadIdx.x; c < f.n; c += blockDim.x) {
-            int i = (int)(c % f.nx);
-            long long t = c / f.nx;
-            int j = (int)(t % f.ny), k = (int)(t / f.ny);
-            long long C = (i / f.cx) + (long long)Cc.g.nx * ((j / f.cy) + (long long)Cc.g.ny * (k / f.cz));
-            L.x[c] += A.omega * Cc.x[C];
+        if (A.post > 0) {
+            // the correction is folded into the first post-smoothing sweep (see rbgs_cell)
+            tail_rbgs<NS, true>(L, false, Cc.x, Cc.g.nx, Cc.g.ny, A.omega);
+            for (int s = 1; s < A.post; s++) tail_rbgs<NS, false>(L, false, nullptr, 0, 0, 0.0);
+        } else {
+            for (long long c = threadIdx.x; c < f.n; c += blockDim.x) {
+                int i = (int)(c % f.nx);
+                long long t = c / f.nx;
+                int j = (int)(t % f.ny), k = (int)(t / f.ny);
+                long long C = (i >> (f.cx - 1)) + (long long)Cc.g.nx * ((j >> (f.cy - 1)) + (long long)Cc.g.ny * (k >> (f.cz - 1)));
+                L.x[c] += A.omega * Cc.x[C];
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        for (int s = 0; s < A.post; s++) tail_rbgs<NS>(L, false);
     }
 }
 
@@ -758,21 +819,23 @@ void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
     MgHier nw;
     auto take = [&](int l, int nx, int ny, int nz) -> MgLevel {
         MgLevel L;
-        if (l < old.nlev && old.lev[l].nx == nx && old.lev[l].ny == ny && old.lev[l].nz == nz) {
+        const long long n = (long long)nx * ny * nz;
+        if (l < old.nlev && old.lev[l].cap >= n) {
             L = old.lev[l];
             old.lev[l] = MgLevel();
         } else {
-            L.nx = nx;
-            L.ny = ny;
-            L.nz = nz;
-            L.n = (long long)nx * ny * nz;
-            L.x = tpb_dalloc<double>(L.n);
-            L.b = tpb_dalloc<double>(L.n);
+            L.cap = n + n / 8 + 64;   // head-room: the coarsening schedule shifts a little between set-ups
+            L.x = tpb_dalloc<double>(L.cap);
+            L.b = tpb_dalloc<double>(L.cap);
             if (l > 0) {
-                L.a = tpb_dalloc<double>((size_t)NS * L.n);
+                L.a = tpb_dalloc<double>((size_t)NS * L.cap);
                 L.own_a = true;
             }
         }
+        L.nx = nx;
+        L.ny = ny;
+        L.nz = nz;
+        L.n = n;
         return L;
     };
     int l = 0;
@@ -831,11 +894,17 @@ void mg_setup(tpb_handle_s* h, MgHier& m, double* a0) {
 }
 
 template <int NS>
-void mg_rbgs(tpb_handle_s* h, const MgLevel& L, bool zero_guess) {
+void mg_rbgs(tpb_handle_s* h, const MgLevel& L, bool zero_guess, const MgLevel* coarse = nullptr, double omega = 0.0) {
     LevGeom g = lg(L);
     long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
     for (int col = 0; col < 2; col++) {
-        rbgs_kernel<NS><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col, (zero_guess && col == 0) ? 1 : 0);
+        if (coarse && col == 0)
+            rbgs_kernel<NS, true><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col, 0, coarse->x, coarse->nx,
+                                                                             coarse->ny, omega);
+        else
+            rbgs_kernel<NS, false><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col,
+                                                                              (zero_guess && col == 0) ? 1 : 0, nullptr, 0, 0,
+                                                                              0.0);
         h->launches++;
     }
 }
@@ -879,9 +948,14 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     for (int l = std::min(ltail, m.nlev - 1) - 1; l >= 0; l--) {
         MgLevel& L = m.lev[l];
         MgLevel& Cc = m.lev[l + 1];
-        prolong_add_kernel<<<nblk(L.n, 256), 256, 0, h->stream>>>(Cc.x, lg(L), lg(Cc), o.mg_overcorrection, L.x);
-        h->launches++;
-        for (int s = 0; s < o.mg_post; s++) mg_rbgs<NS>(h, L, false);
+        if (o.mg_post > 0) {
+            // coarse correction folded into the first post-smoothing sweep (see rbgs_cell)
+            mg_rbgs<NS>(h, L, false, &Cc, o.mg_overcorrection);
+            for (int s = 1; s < o.mg_post; s++) mg_rbgs<NS>(h, L, false);
+        } else {
+            prolong_add_kernel<<<nblk(L.n, 256), 256, 0, h->stream>>>(Cc.x, lg(L), lg(Cc), o.mg_overcorrection, L.x);
+            h->launches++;
+        }
     }
 }
 
@@ -1073,6 +1147,9 @@ void tpb_pc_free(tpb_handle_s* h) {
     tpb_dfree(pc->t2);
     tpb_dfree(pc->t3);
     tpb_dfree(pc->strength);
+    if (pc->gexec) cudaGraphExecDestroy(pc->gexec);
+    tpb_dfree(pc->gx);
+    tpb_dfree(pc->gy);
     delete pc;
     h->pc = nullptr;
 }
@@ -1092,10 +1169,57 @@ void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double
     DISPATCH(pc_setup_t, h, J, u, dt);
     TPB_CUDA(cudaGetLastError());
     h->pc->ready = true;
+    // Capture one application into a CUDA graph (single-rank slabs only: the multi-rank apply contains NCCL
+    // halo exchanges).  The Krylov loop applies the PC 20-30 times per set-up; replaying removes the host-side
+    // launch cost of its ~100 small kernels.  TPB_GRAPH=0 disables it.
+    PcState* pc = h->pc;
+    pc->graph_ok = false;
+    static const bool want = !(getenv("TPB_GRAPH") && atoi(getenv("TPB_GRAPH")) == 0);
+    const bool any = h->opts.stage1 != TPB_S1_NONE || h->opts.stage2 != TPB_S2_NONE;
+    if (want && any && !(h->g.has_lo || h->g.has_hi)) {
+        const size_t nd = (size_t)h->nf * h->g.n;
+        if (!pc->gx) pc->gx = tpb_dalloc<double>(nd);
+        if (!pc->gy) pc->gy = tpb_dalloc<double>(nd);
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = h->launches;
+        TPB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            DISPATCH(pc_apply_t, h, pc->gx, pc->gy);
+        } catch (...) {
+            cudaStreamEndCapture(h->stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        TPB_CUDA(cudaStreamEndCapture(h->stream, &graph));
+        pc->graph_nodes = h->launches - l0;
+        h->launches = l0;
+        bool updated = false;
+        if (pc->gexec) {
+            cudaGraphExecUpdateResultInfo info;
+            updated = cudaGraphExecUpdate(pc->gexec, graph, &info) == cudaSuccess;
+            if (!updated) {
+                cudaGetLastError();
+                cudaGraphExecDestroy(pc->gexec);
+                pc->gexec = nullptr;
+            }
+        }
+        if (!updated) TPB_CUDA(cudaGraphInstantiate(&pc->gexec, graph, 0));
+        cudaGraphDestroy(graph);
+        pc->graph_ok = true;
+    }
 }
 
 void tpb_pc_apply_impl(tpb_handle_s* h, const double* x, double* y) {
     TPB_REQUIRE(h->pc && h->pc->ready, TPB_ERR_STATE, "tpb_pc_apply before tpb_pc_setup");
+    PcState* pc = h->pc;
+    if (pc->graph_ok) {
+        const size_t nd = (size_t)h->nf * h->g.n;
+        TPB_CUDA(cudaMemcpyAsync(pc->gx, x, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        TPB_CUDA(cudaGraphLaunch(pc->gexec, h->stream));
+        TPB_CUDA(cudaMemcpyAsync(y, pc->gy, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        h->launches += pc->graph_nodes;
+        return;
+    }
     DISPATCH(pc_apply_t, h, x, y);
     TPB_CUDA(cudaGetLastError());
 }

@@ -67,6 +67,20 @@ void tpb_ksp_solve_impl(tpb_handle_s* h, const double* J, const double* b, doubl
         h->ksp->wv = tpb_dalloc<double>(nd);
     }
     KspState& K = *h->ksp;
+    if (K.Vc.empty()) {
+        // Reserve the Krylov basis up front so that no cudaMalloc (tens of ms for a 32-vector chunk) lands inside
+        // a solve: the full restart length when it fits in 30 % of the free memory (SPE10: 201 x 27 MB), else as
+        // many chunks as that budget holds; the rest is still allocated on demand.
+        size_t free_b = 0, total_b = 0;
+        TPB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_vec = nd * sizeof(double) * (flex ? 2 : 1);
+        size_t nvec = (size_t)(0.30 * (double)free_b) / per_vec;
+        if (nvec > (size_t)m + 1) nvec = (size_t)m + 1;
+        for (size_t j = 0; j < nvec; j += CHUNK) {
+            vec_at(K.Vc, nd, (int)j);
+            if (flex) vec_at(K.Zc, nd, (int)j);
+        }
+    }
     K.H.assign((size_t)(m + 1) * m, 0.0);
     K.cs.assign(m, 0.0);
     K.sn.assign(m, 0.0);
