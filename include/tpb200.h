@@ -110,6 +110,7 @@ typedef struct {
     int mg_cycles;            /* V-cycles per application (pc_hypre_boomeramg_max_iter) */
     double mg_semi_theta;     /* an axis is coarsened on a level only if its mean coupling is at least
                                  theta * the strongest axis' (0 = always coarsen every axis) */
+    int mg_full_below;        /* levels with at most this many cells coarsen every axis (0 = never) */
     /* second stage: block ILU(0) of the nf x nf block stencil in red-black ordering, one block per
      * rank as PETSc bjacobi+ilu (the slab couplings to other ranks are dropped) */
     int verbose;

@@ -605,7 +605,7 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
             if (dims[ax] > 1 && m_ax[ax] > mmax) mmax = m_ax[ax];
         int cf[3] = {1, 1, 1}, any = 0;
         for (int ax = 0; ax < 3; ax++)
-            if (dims[ax] > 1 && m_ax[ax] >= o->mg_semi_theta * mmax) {
+            if (dims[ax] > 1 && (m_ax[ax] >= o->mg_semi_theta * mmax || L->n <= o->mg_full_below)) {
                 cf[ax] = 2;
                 any = 1;
             }

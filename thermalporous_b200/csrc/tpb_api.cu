@@ -289,13 +289,14 @@ int tpb_solver_defaults(int nphase, tpb_solver_opts* o) {
     o->decoup = TPB_DECOUP_NO;
     o->schur_pre = TPB_SCHUR_CONVDIFF;
     o->stage2 = TPB_S2_ILU0;
-    o->mg_pre = 1;
-    o->mg_post = 1;
+    o->mg_pre = 2;
+    o->mg_post = 2;
     o->mg_coarse_sweeps = 4;
     o->mg_min_cells = 8;
     o->mg_overcorrection = 1.0;
     o->mg_cycles = 1;
     o->mg_semi_theta = 0.5;
+    o->mg_full_below = 0;
     o->verbose = 0;
     return TPB_OK;
 }

@@ -436,9 +436,9 @@ __global__ void __launch_bounds__(128) coarsen_op_kernel(const double* __restric
 // old value, so after a correction x += omega P xc only the OTHER colour's corrected values matter, and they
 // are formed on the fly as x[nb] + omega xc[aggregate(nb)] (saves the prolongation pass over x entirely).
 template <int NS, bool PROLONG>
-__device__ __forceinline__ void rbgs_cell(const double* __restrict__ a, const double* __restrict__ b, double* x,
+__device__ __forceinline__ void rbgs_cell(const double* __restrict__ a, const double* b, double* x,
                                           const LevGeom& g, int i, int j, int k, bool zero_guess,
-                                          const double* __restrict__ xc, int cnx, int cny, double omega) {
+                                          const double* xc, int cnx, int cny, double omega) {
     long long c = i + (long long)g.nx * (j + (long long)g.ny * k);
     double acc = b[c];
     if (!zero_guess) {
@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a,
 // fully unrolled 2x2x2 box with predication so that the loads of all its fine cells are in flight together;
 // the summation order (k, j, i; within a cell diag, x-, x+, ...) is the one the CPU restatement uses.
 template <int NS>
-__device__ __forceinline__ double restrict_cell(const double* __restrict__ a, const double* __restrict__ b,
-                                                const double* __restrict__ x, const LevGeom& f, int I, int Jc, int Kc) {
+__device__ __forceinline__ double restrict_cell(const double* __restrict__ a, const double* b, const double* x,
+                                                const LevGeom& f, int I, int Jc, int Kc) {
     double r[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -569,13 +569,24 @@ struct TailArgs {
     double omega;
 };
 
-template <int NS, bool PROLONG>
-__device__ void tail_rbgs(const TailLevel& L, bool zero_guess, const double* xc, int cnx, int cny, double omega) {
+// The sub-V-cycle over a run of levels inside one kernel; the barrier between colour passes is a template
+// parameter.  Measured on B200 (60x220x85, r1): sharing the levels of <= 160 k cells among a co-resident
+// cooperative grid (grid.sync) was no faster than one launch per pass replayed from a CUDA graph, and one
+// 8-CTA thread-block cluster (cluster.sync) was 12 % slower (too little memory-level parallelism), so only the
+// single-CTA tail (levels <= TAIL_CELLS, __syncthreads) is kept.  Level vectors b, x are written and re-read
+// inside the same kernel, so they are plain pointers here (no __restrict__/read-only path).
+struct BlockBarrier {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+template <int NS, bool PROLONG, class Barrier>
+__device__ __forceinline__ void cyc_sweep(const TailLevel& L, bool zero_guess, const double* xc, int cnx, int cny,
+                                          double omega, long long tid, long long nth, Barrier& bar) {
     const LevGeom& g = L.g;
     const int nxh = (g.nx + 1) >> 1;
     const long long total = (long long)g.ny * g.nz * nxh;
     for (int col = 0; col < 2; col++) {
-        for (long long t = threadIdx.x; t < total; t += blockDim.x) {
+        for (long long t = tid; t < total; t += nth) {
             int ih = (int)(t % nxh);
             long long row = t / nxh;
             int j = (int)(row % g.ny), k = (int)(row / g.ny);
@@ -587,49 +598,62 @@ __device__ void tail_rbgs(const TailLevel& L, bool zero_guess, const double* xc,
                     rbgs_cell<NS, false>(L.a, L.b, L.x, g, i, j, k, zero_guess && col == 0, nullptr, 0, 0, 0.0);
             }
         }
-        __syncthreads();
+        bar();
     }
 }
 
-template <int NS>
-__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
-    // down
-    for (int l = 0; l < A.nlev - 1; l++) {
+// levels l0 .. l1-1: pre-smooth, restrict the residual into level l+1
+template <int NS, class Barrier>
+__device__ __forceinline__ void cyc_down(const TailArgs& A, int l0, int l1, long long tid, long long nth, Barrier& bar) {
+    for (int l = l0; l < l1; l++) {
         const TailLevel& L = A.lev[l];
-        for (int s = 0; s < A.pre; s++) tail_rbgs<NS, false>(L, s == 0, nullptr, 0, 0, 0.0);
+        for (int s = 0; s < A.pre; s++) cyc_sweep<NS, false>(L, s == 0, nullptr, 0, 0, 0.0, tid, nth, bar);
         const TailLevel& Cc = A.lev[l + 1];
-        for (long long C = threadIdx.x; C < Cc.g.n; C += blockDim.x) {
+        for (long long C = tid; C < Cc.g.n; C += nth) {
             int I = (int)(C % Cc.g.nx);
             long long t = C / Cc.g.nx;
             Cc.b[C] = restrict_cell<NS>(L.a, L.b, L.x, L.g, I, (int)(t % Cc.g.ny), (int)(t / Cc.g.ny));
         }
-        __syncthreads();
+        bar();
     }
-    // coarsest
-    {
-        const TailLevel& L = A.lev[A.nlev - 1];
-        for (int s = 0; s < A.coarse_sweeps; s++) tail_rbgs<NS, false>(L, s == 0, nullptr, 0, 0, 0.0);
-    }
-    // up
-    for (int l = A.nlev - 2; l >= 0; l--) {
+}
+
+template <int NS, class Barrier>
+__device__ __forceinline__ void cyc_coarsest(const TailArgs& A, long long tid, long long nth, Barrier& bar) {
+    const TailLevel& L = A.lev[A.nlev - 1];
+    for (int s = 0; s < A.coarse_sweeps; s++) cyc_sweep<NS, false>(L, s == 0, nullptr, 0, 0, 0.0, tid, nth, bar);
+}
+
+// levels l1-1 down to l0: coarse correction (folded into the first post-smoothing sweep) + post-smoothing
+template <int NS, class Barrier>
+__device__ __forceinline__ void cyc_up(const TailArgs& A, int l1, int l0, long long tid, long long nth, Barrier& bar) {
+    for (int l = l1 - 1; l >= l0; l--) {
         const TailLevel& L = A.lev[l];
         const TailLevel& Cc = A.lev[l + 1];
         const LevGeom& f = L.g;
         if (A.post > 0) {
-            // the correction is folded into the first post-smoothing sweep (see rbgs_cell)
-            tail_rbgs<NS, true>(L, false, Cc.x, Cc.g.nx, Cc.g.ny, A.omega);
-            for (int s = 1; s < A.post; s++) tail_rbgs<NS, false>(L, false, nullptr, 0, 0, 0.0);
+            cyc_sweep<NS, true>(L, false, Cc.x, Cc.g.nx, Cc.g.ny, A.omega, tid, nth, bar);
+            for (int s = 1; s < A.post; s++) cyc_sweep<NS, false>(L, false, nullptr, 0, 0, 0.0, tid, nth, bar);
         } else {
-            for (long long c = threadIdx.x; c < f.n; c += blockDim.x) {
+            for (long long c = tid; c < f.n; c += nth) {
                 int i = (int)(c % f.nx);
                 long long t = c / f.nx;
                 int j = (int)(t % f.ny), k = (int)(t / f.ny);
                 long long C = (i >> (f.cx - 1)) + (long long)Cc.g.nx * ((j >> (f.cy - 1)) + (long long)Cc.g.ny * (k >> (f.cz - 1)));
                 L.x[c] += A.omega * Cc.x[C];
             }
-            __syncthreads();
+            bar();
         }
     }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
+    BlockBarrier bar;
+    const long long tid = threadIdx.x, nth = blockDim.x;
+    cyc_down<NS>(A, 0, A.nlev - 1, tid, nth, bar);
+    cyc_coarsest<NS>(A, tid, nth, bar);
+    cyc_up<NS>(A, A.nlev - 1, 0, tid, nth, bar);
 }
 
 // ---- K6 / coupling kernels ----------------------------------------------------------------------
@@ -860,7 +884,7 @@ void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
         int cf[3] = {1, 1, 1};
         bool any = false;
         for (int ax = 0; ax < 3; ax++)
-            if (dims[ax] > 1 && m_ax[ax] >= o.mg_semi_theta * mmax) {
+            if (dims[ax] > 1 && (m_ax[ax] >= o.mg_semi_theta * mmax || L.n <= o.mg_full_below)) {
                 cf[ax] = 2;
                 any = true;
             }
@@ -914,11 +938,12 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     const tpb_solver_opts& o = h->opts;
     const int pre = o.mg_pre > 0 ? o.mg_pre : 1;
     const int coarse = o.mg_coarse_sweeps > 0 ? o.mg_coarse_sweeps : 1;
-    // first level that fits the single-CTA tail
+    // level zones: [0, lcoop) one kernel per colour pass, [lcoop, nlev) inside one CTA (the tail)
     int ltail = m.nlev - 1;
     while (ltail > 0 && m.lev[ltail - 1].n <= TAIL_CELLS) ltail--;
     if (m.lev[ltail].n > TAIL_CELLS) ltail = m.nlev;  // no tail at all (coarsest too large)
-    for (int l = 0; l < ltail && l < m.nlev; l++) {
+    const int lcoop = ltail;
+    for (int l = 0; l < lcoop && l < m.nlev; l++) {
         MgLevel& L = m.lev[l];
         if (l == m.nlev - 1) {
             for (int s = 0; s < coarse; s++) mg_rbgs<NS>(h, L, s == 0);
@@ -929,14 +954,14 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         restrict_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
         h->launches++;
     }
-    if (ltail < m.nlev) {
+    if (lcoop < m.nlev) {
         TailArgs A;
-        A.nlev = m.nlev - ltail;
-        for (int l = ltail; l < m.nlev; l++) {
-            A.lev[l - ltail].g = lg(m.lev[l]);
-            A.lev[l - ltail].a = m.lev[l].a;
-            A.lev[l - ltail].x = m.lev[l].x;
-            A.lev[l - ltail].b = m.lev[l].b;
+        A.nlev = m.nlev - lcoop;
+        for (int l = lcoop; l < m.nlev; l++) {
+            A.lev[l - lcoop].g = lg(m.lev[l]);
+            A.lev[l - lcoop].a = m.lev[l].a;
+            A.lev[l - lcoop].x = m.lev[l].x;
+            A.lev[l - lcoop].b = m.lev[l].b;
         }
         A.pre = pre;
         A.post = o.mg_post;
@@ -945,7 +970,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         tail_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(A);
         h->launches++;
     }
-    for (int l = std::min(ltail, m.nlev - 1) - 1; l >= 0; l--) {
+    for (int l = std::min(lcoop, m.nlev - 1) - 1; l >= 0; l--) {
         MgLevel& L = m.lev[l];
         MgLevel& Cc = m.lev[l + 1];
         if (o.mg_post > 0) {
