@@ -274,19 +274,26 @@ def run_b200(args):
         diff = max(float(np.abs(dev_final[f] - hu_np[f]).max() / np.abs(dev_final[f]).max()) for f in range(3))
         e2e["max_rel_diff_vs_resident_run"] = diff
 
-    # ---- roofline of the two kernels north_star names, timed alone with CUDA events on the handle's stream
+    # ---- rooflines, each kernel timed alone with CUDA events on the handle's stream (burst peak applies)
     pk, pk_how = peak_gbs()
     F = eng.empty(3, n_loc)
     J = eng.empty(7, 3, 3, n_loc)
     x = torch.randn(3, n_loc, device=eng.device, dtype=torch.float64)
     y = eng.empty(3, n_loc)
+    eng.assemble(u, uo, res.dt_vec[-1], F=F, J=J)
+    eng.pc_setup(J, u, res.dt_vec[-1])
     roof = {}
-    for which, name in ((0, "assemble_FJ"), (2, "spmv")):
+    # per-launch DRAM traffic from the committed `ncu --set full` captures (profiles/r1_ncu_full_summary.md)
+    traffic = {"spmv": 594.5e6 if n_loc == 1122000 else None, "assemble_FJ": None, "rbgs_fine": 83.1e6 if n_loc == 1122000 else None}
+    for which, name, bpc, units in ((0, "assemble_FJ", BYTES["assemble_FJ"], n_loc), (2, "spmv", BYTES["spmv"], n_loc),
+                                    (3, "rbgs_fine", 80, n_loc // 2)):
         t_ms = eng.time_kernel(which, u, uo, res.dt_vec[-1], F, J, x, y, reps=20)
-        gbs = BYTES[name] * n_loc / t_ms / 1e6
-        roof[name] = {"bound": "hbm", "achieved": gbs, "peak": pk, "unit": "GB/s", "frac": gbs / pk, "traffic": None,
-                      "ms_per_launch": t_ms, "bytes_per_cell": BYTES[name], "cells_per_launch": n_loc, "peak_source": pk_how}
-
+        gbs = bpc * units / t_ms / 1e6
+        roof[name] = {"bound": "hbm", "achieved": gbs, "peak": pk, "unit": "GB/s", "frac": gbs / pk, "traffic": traffic[name],
+                      "ms_per_launch": t_ms, "bytes_per_unit": bpc, "units_per_launch": units, "peak_source": pk_how}
+    roof["assemble_FJ"]["note"] = "property pre-pass + flux kernel + source kernel (3 launches)"
+    roof["rbgs_fine"]["note"] = ("one colour pass of the fine-level pressure smoother: the kernel with the largest share of the step "
+                                 "(profiles/r1_launch_summary.md); 80 B per updated cell, half the cells per pass")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -297,13 +304,14 @@ def run_b200(args):
             "failed_solves": res.failed_solves, "host_wall_ms_per_step": wall * 1e3 / args.steps,
             "phase_ms": {"assemble": sum(s.t_assemble_ms for s in res.stats), "pc_setup": sum(s.t_pcsetup_ms for s in res.stats),
                          "ksp": sum(s.t_ksp_ms for s in res.stats)},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof["spmv"], "roofline_assembly": roof["assemble_FJ"]}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof["spmv"], "roofline_assembly": roof["assemble_FJ"],
+            "roofline_dominant_by_share": roof["rbgs_fine"]}
     if e2e is not None:
         line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu:
-        cval, csec, cres, threads, cn = cpu_run(CPU_SAMPLE_NZ, 2, 1)
+        cval, csec, cres, threads, cn = cpu_run(CPU_SAMPLE_NZ, 6, 2)
         line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "top %d of %d layers (%d cells), 2 steps after 1 warm-up, oracle/cport C+OpenMP "
+                                "sample": "top %d of %d layers (%d cells), 6 steps after 2 warm-up, oracle/cport C+OpenMP "
                                           "restatement of the same path (%.1f s)" % (CPU_SAMPLE_NZ, NZ, cn, csec)}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -194,7 +194,8 @@ int tpb_pc_get_weights(tpb_handle h, int f, double* out);                      /
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t tpb_launch_count(tpb_handle h);
 /* timing of the dominant kernels with CUDA events on the handle's stream: runs `reps` launches
- * of kernel `which` (0 assemble F+J, 1 assemble F, 2 spmv) and returns the mean ms per launch */
+ * of kernel `which` (0 assemble F+J [property pre-pass + flux kernel + sources], 1 assemble F, 2 spmv,
+ * 3 one colour pass of the fine-level pressure smoother; needs tpb_pc_setup) and returns the mean ms per launch */
 int tpb_time_kernel(tpb_handle h, int which, const double* u, const double* u_old, double dt,
                     double* F, double* J, const double* x, double* y, int reps, double* ms);
 void* tpb_stream(tpb_handle h);

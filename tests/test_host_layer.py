@@ -143,3 +143,37 @@ def test_time_loop_failure_halves_dt_and_restores_state():
     assert u[0, 0] == 1.0 and np.all(u[2] == 0.9) and np.array_equal(u, uo)
     with pytest.raises(ConvergenceError):
         raise ConvergenceError(-3)
+
+
+def test_spe10_dat_round_trip_and_slicing(tmp_path):
+    """spe_*.dat layout (x fastest, layers top-down, 3 permeability blocks) and the slice arrays the reference's
+    SPE10 geo classes load (data/create_SPE10_slice.py:23-71, create_SPE10_slice2D.py:11-60)."""
+    from thermalporous_b200 import spe10data as D
+    rng = np.random.default_rng(0)
+    shp = (D.NZ, D.NY, D.NX)
+    phi, kx, ky, kz = (np.round(rng.random(shp), 6) for _ in range(4))
+    D.write_dat(str(tmp_path), phi, kx, ky, kz)
+    got = D.read_dat(str(tmp_path))
+    for a, b in zip(got, (phi, kx, ky, kz)):
+        assert np.array_equal(a, b)
+    s_phi, s_kx, s_ky, s_kz = D.create_slice(8, 16, 5, x_shift=3, y_shift=7, z_shift=2, fields=got, save_dir=str(tmp_path))
+    # the reference's triple loop, literally
+    line = phi.reshape(-1)
+    kline = kz.reshape(-1) * 9.869233e-10
+    for (i, j, kk) in ((0, 0, 0), (7, 15, 4), (2, 9, 3)):
+        src = (i + 3) + (j + 7) * 60 + (kk + 2) * 220 * 60
+        assert s_phi[i, j, 5 - 1 - kk] == line[src] and s_kz[i, j, 5 - 1 - kk] == kline[src]
+    prm = params()
+    geo = G.SPE10Model3D(8, 16, 5, prm, data_dir=str(tmp_path))         # loads the slice_*.npy just written
+    assert geo.K_z[2 + 8 * (9 + 16 * 1)] == s_kz[2, 9, 1]
+    p2, kx2, ky2 = D.create_slice2D(6, 9, x_shift=1, y_shift=2, z_shift=4, fields=got)
+    assert p2[3, 5] == line[(3 + 1) + (5 + 2) * 60 + 4 * 220 * 60] and p2.shape == (6, 9)
+
+
+def test_checkpoint_round_trip(tmp_path):
+    from thermalporous_b200.model import load_checkpoint, save_checkpoint
+    u = np.random.default_rng(1).random((3, 40))
+    save_checkpoint(str(tmp_path / "chk"), u)
+    assert np.array_equal(load_checkpoint(str(tmp_path / "chk"), (3, 40)), u)
+    with pytest.raises(ValueError):
+        load_checkpoint(str(tmp_path / "chk"), (2, 40))

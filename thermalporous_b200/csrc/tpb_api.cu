@@ -17,6 +17,7 @@ int tpb_pc_mg_level_impl(tpb_handle_s* h, int which, int l, int* dims6, double* 
 void tpb_pc_mg_apply_impl(tpb_handle_s* h, int which, const double* b, double* y);
 void tpb_pc_stage2_apply_impl(tpb_handle_s* h, const double* r, double* z);
 const double* tpb_pc_weights_impl(tpb_handle_s* h, int f);
+long long tpb_pc_rbgs_pass_impl(tpb_handle_s* h, int col);
 
 static thread_local std::string g_err;
 
@@ -478,6 +479,8 @@ int tpb_time_kernel(tpb_handle h, int which, const double* u, const double* u_ol
             tpb_launch_assemble(h, u, u_old, dt, F, J);
         else if (which == 1)
             tpb_launch_assemble(h, u, u_old, dt, F, nullptr);
+        else if (which == 3)
+            tpb_pc_rbgs_pass_impl(h, 1);
         else
             tpb_launch_spmv(h, J, x, y);
     };

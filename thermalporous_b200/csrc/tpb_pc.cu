@@ -1288,3 +1288,17 @@ void tpb_pc_stage2_apply_impl(tpb_handle_s* h, const double* r, double* z) {
     }
 }
 const double* tpb_pc_weights_impl(tpb_handle_s* h, int f) { return h->pc ? h->pc->w[f] : nullptr; }
+
+// one colour pass of the fine-level pressure smoother on its own (bench.py roofline of the dominant kernel)
+long long tpb_pc_rbgs_pass_impl(tpb_handle_s* h, int col) {
+    TPB_REQUIRE(h->pc && h->pc->ready && h->pc->mg_p.nlev > 0, TPB_ERR_STATE, "pressure multigrid not set up");
+    const MgLevel& L = h->pc->mg_p.lev[0];
+    LevGeom g = lg(L);
+    long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
+    if (h->ns == 7)
+        rbgs_kernel<7, false><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col, 0, nullptr, 0, 0, 0.0);
+    else
+        rbgs_kernel<5, false><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col, 0, nullptr, 0, 0, 0.0);
+    h->launches++;
+    return threads;
+}

@@ -131,6 +131,19 @@ def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_
     return res
 
 
+def save_checkpoint(name, u):
+    """store the solution fields (nf, ncell) - stands in for DumbCheckpoint.store (thermalmodel.py:361-364)."""
+    np.savez(name if name.endswith(".npz") else name + ".npz", solution=np.asarray(u))
+
+
+def load_checkpoint(name, shape=None):
+    z = np.load(name if name.endswith(".npz") else name + ".npz")
+    u = z["solution"]
+    if shape is not None and tuple(u.shape) != tuple(shape):
+        raise ValueError("checkpoint %s holds %s, the model needs %s" % (name, u.shape, tuple(shape)))
+    return u
+
+
 class _TorchOps:
     def __init__(self, engine):
         self.e = engine
@@ -155,8 +168,10 @@ class ThermalModel:
         from . import _lib as L
         if save:
             raise NotImplementedError("pvd/VTK output is outside the hot path (SURVEY.md 8f)")
-        if checkpointing and (checkpointing.get("save") or checkpointing.get("load")):
-            raise NotImplementedError("HDF5 checkpoints are outside the hot path (SURVEY.md 8f)")
+        # thermalmodel.py:20-21; the reference stores the solution with DumbCheckpoint (HDF5) - here a .npz of
+        # the fields in the C-ABI cell order
+        self.checkpointing = {"save": False, "load": False, "savename": "initial", "loadname": "initial"}
+        self.checkpointing.update(checkpointing or {})
         self.maxdt, self.dt_init_fact, self.end, self.verbosity = maxdt, dt_init_fact, end, verbosity
         self.filename = filename
         geo, prm = self.geo, self.params
@@ -185,7 +200,11 @@ class ThermalModel:
 
     def solve(self, max_steps=None):
         e = self.engine
-        self.u.copy_(e.tensor(self.initial_condition))
+        if self.checkpointing["load"]:                           # thermalmodel.py:87-91
+            self.resultprint("Using as initial solution checkpoint " + self.checkpointing["loadname"])
+            self.u.copy_(e.tensor(load_checkpoint(self.checkpointing["loadname"], self.u.shape)))
+        else:
+            self.u.copy_(e.tensor(self.initial_condition))
         self.u_.copy_(self.u)
         res = run_time_loop(lambda u, uo, dt: e.newton_solve(u, uo, dt), _TorchOps(e), self.u, self.u_,
                             end=self.end, maxdt=self.maxdt, small_dt_start=self.small_dt_start,
@@ -194,6 +213,9 @@ class ThermalModel:
         self.result = res
         self.total_nits, self.total_lits = res.total_nits, res.total_lits
         self.last_dt = res.dt_vec[-1] if res.dt_vec else None
+        if self.checkpointing["save"]:                           # thermalmodel.py:361-364
+            save_checkpoint(self.checkpointing["savename"], self.u.detach().cpu().numpy())
+            self.resultprint("Saving checkpoint solution in " + self.checkpointing["savename"])
         if self.verbosity and res.dt_vec:                       # thermalmodel.py:367-408
             p = self.resultprint
             p("nits = ", res.nits_vec, ";")
