@@ -37,9 +37,10 @@ BYTES = {"assemble_FJ": 608, "spmv": 552}   # algorithmic B/cell, 3-D two-phase 
 CPU_SAMPLE_NZ = 17
 
 
-def workload_name(nz, refine):
+def workload_name(nz, mult, mode="stack"):
+    how = "" if mult == 1 else (", %d stacked copies of the 85-layer column" % mult if mode == "stack" else ", z-refined x%d" % mult)
     return ("SPE10-shaped synthetic 60x220x%d (seed 10%s) TwoPhase thermal, wells 'default' Peaceman rate 2e-4, "
-            "S_o=0.9, %s, small_dt_start 2^-10 of maxdt=1 day" % (nz, ", z-refined x%d" % refine if refine > 1 else "", PC))
+            "S_o=0.9, %s, small_dt_start 2^-10 of maxdt=1 day" % (nz, how, PC))
 
 
 def make_params():
@@ -52,12 +53,18 @@ def make_params():
     return p
 
 
-def make_geo(prm, nz_layers=NZ, refine=1):
+def make_geo(prm, nz_layers=NZ, mult=1, mode="stack"):
+    """mult > 1 (weak scaling, one 85-layer slab per rank): 'stack' = mult copies of the column on top of each other
+    (same cells, same physics per slab), 'refine' = every layer split mult times (BASELINE config 5; smaller cells
+    make the same wells a harder problem, so it mixes solver difficulty into the scaling number)."""
     from thermalporous_b200 import geo as G
     fields = G.spe10_synthetic(NX, NY, NZ, seed=10)
     if nz_layers != NZ:
         fields = [np.ascontiguousarray(f[:, :, NZ - nz_layers:]) for f in fields]   # the top nz_layers layers (z up)
-    return G.SPE10Model3D(NX, NY, nz_layers, prm, fields=fields, refine_z=refine)
+    if mult > 1 and mode == "stack":
+        fields = [np.concatenate([f] * mult, axis=2) for f in fields]
+        return G.SPE10Model3D(NX, NY, nz_layers * mult, prm, fields=fields)
+    return G.SPE10Model3D(NX, NY, nz_layers, prm, fields=fields, refine_z=mult)
 
 
 class ClockSampler:
@@ -194,7 +201,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     prm = make_params()
     refine = world
-    geo = make_geo(prm, NZ, refine)                 # global grid 60 x 220 x 85*world, Dz/world
+    geo = make_geo(prm, NZ, world, args.scale)      # global grid 60 x 220 x 85*world
     from thermalporous_b200.partition import Slab
     slab = Slab(geo, world, rank)
     case = CS.WellCase(prm, geo, well_case="default")
@@ -297,7 +304,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(geo.Nz, refine), "cells": n_glob, "cells_per_gpu": n_loc,
+            "config": {"workload": workload_name(geo.Nz, refine, args.scale), "cells": n_glob, "cells_per_gpu": n_loc,
                        "solver": desc, "l2": "working set per Newton step (Jacobian 565 MB + Krylov basis) exceeds the 126 MB L2; no flush needed",
                        "parallelism": "z-slab x%d" % world},
             "nits": res.nits_vec, "lits": res.lits_vec, "dt_days": [d / 86400.0 for d in res.dt_vec],
@@ -327,6 +334,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scale", default="stack", choices=["stack", "refine"], help="how the grid grows with --gpus (weak scaling)")
     ap.add_argument("--opt", action="append", default=[], help="solver option override key=value (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
