@@ -52,6 +52,8 @@ int tpb_create(const tpb_grid* grid, int nphase, const tpb_params* prm, int devi
         TPB_REQUIRE(grid->dim == 2 || grid->dim == 3, TPB_ERR_ARG, "dim must be 2 or 3");
         TPB_REQUIRE(grid->nx > 0 && grid->ny > 0 && grid->nz > 0, TPB_ERR_ARG, "empty grid");
         TPB_REQUIRE(grid->dim == 3 || grid->nz == 1, TPB_ERR_ARG, "2-D grids need nz == 1");
+        TPB_REQUIRE((double)grid->nx * grid->ny * ((double)grid->nz + 2.0) < 2147483647.0, TPB_ERR_ARG,
+                    "a slab must hold fewer than 2^31 cells (kernels index cells in 32 bits); use more slabs");
         int ndev = 0;
         TPB_CUDA(cudaGetDeviceCount(&ndev));
         TPB_REQUIRE(device >= 0 && device < ndev, TPB_ERR_CUDA, "no such CUDA device (libtpb200 has no CPU fallback)");

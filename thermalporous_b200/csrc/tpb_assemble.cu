@@ -78,9 +78,8 @@ __global__ void __launch_bounds__(256) trans_kernel(GField Kx, GField Ky, GField
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int nx = g.nx, ny = g.ny, np = g.np;
-    int i = (int)(c % nx);
-    long long t = c / nx;
-    int j = (int)(t % ny), k = (int)(t / ny);
+    int i, j, k;
+    tpb_ijk(c, nx, ny, i, j, k);
     tx[c] = i < nx - 1 ? g.area[0] * harm(Kx.v[c], Kx.v[c + 1]) : 0.0;
     if (DIM == 2) {
         bool ex = j < ny - 1 || g.has_hi;
@@ -240,10 +239,8 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
     if (cell >= n) return;
     const int nx = g.nx, ny = g.ny, np = g.np;
     const long long ne = n + 2LL * np;
-    int i = (int)(cell % nx);
-    long long t = cell / nx;
-    int j = (int)(t % ny);
-    int k = (int)(t / ny);
+    int i, j, k;
+    tpb_ijk(cell, nx, ny, i, j, k);
 
     const Side<NF> me = load_side<NF, false>(P, fl, scr, n, np, ne, cell);
     const double phi = fl.phi.v[cell];

@@ -60,6 +60,17 @@ struct GField {
 
 __host__ __device__ inline int tpb_ns(int dim) { return dim == 3 ? 7 : 5; }
 
+// (i, j, k) of a linear index in 32-bit arithmetic: a slab holds fewer than 2^31 cells (checked in tpb_create), and
+// 64-bit integer division is emulated on the GPU - two of them cost more than the rest of a small stencil kernel
+__device__ __forceinline__ void tpb_ijk(long long c, int nx, int ny, int& i, int& j, int& k) {
+    const unsigned cu = (unsigned)c;
+    const unsigned t = cu / (unsigned)nx;
+    i = (int)(cu - t * (unsigned)nx);
+    const unsigned kk = t / (unsigned)ny;
+    j = (int)(t - kk * (unsigned)ny);
+    k = (int)kk;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward-mode dual numbers (value + N partials); everything is unrolled into registers
 // ---------------------------------------------------------------------------------------------

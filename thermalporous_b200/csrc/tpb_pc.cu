@@ -127,9 +127,8 @@ __global__ void __launch_bounds__(128) cpr_setup_kernel(const double* __restrict
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
-    int i = (int)(c % nx);
-    long long t = c / nx;
-    int j = (int)(t % ny), k = (int)(t / ny);
+    int i, j, k;
+    tpb_ijk(c, nx, ny, i, j, k);
     constexpr int L = NF - 1;
     double wf[TPB_MAXF] = {0.0, 0.0, 0.0};
     if (dec == TPB_DECOUP_QI) {
@@ -177,9 +176,8 @@ __global__ void __launch_bounds__(128) cptr_setup_kernel(const double* __restric
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
-    int i = (int)(c % nx);
-    long long t = c / nx;
-    int j = (int)(t % ny), k = (int)(t / ny);
+    int i, j, k;
+    tpb_ijk(c, nx, ny, i, j, k);
     double wa[2] = {0.0, 0.0};
     if (NF == 3 && dec == TPB_DECOUP_QI) {
         double dss = JAT(0, NF - 1, NF - 1, c);
@@ -248,9 +246,8 @@ __global__ void __launch_bounds__(128) convdiff_kernel(const double* __restrict_
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
-    int i = (int)(c % nx);
-    long long t = c / nx;
-    int j = (int)(t % ny), k = (int)(t / ny);
+    int i, j, k;
+    tpb_ijk(c, nx, ny, i, j, k);
     double phi = phi_f[c];
     CdCell me = cd_props<NF>(P, u, n, c, phi, NF == 2 ? kT_f[c] : 0.0);
     double diag;
@@ -401,9 +398,8 @@ __global__ void __launch_bounds__(128) coarsen_op_kernel(const double* __restric
                                                          double* __restrict__ ac) {
     long long C = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (C >= cg.n) return;
-    int I = (int)(C % cg.nx);
-    long long t = C / cg.nx;
-    int Jc = (int)(t % cg.ny), Kc = (int)(t / cg.ny);
+    int I, Jc, Kc;
+    tpb_ijk(C, cg.nx, cg.ny, I, Jc, Kc);
     double acc[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) acc[s] = 0.0;
@@ -472,9 +468,8 @@ __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a,
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long rows = (long long)g.ny * g.nz;
     if (t >= rows * nxh) return;
-    int ih = (int)(t % nxh);
-    long long row = t / nxh;
-    int j = (int)(row % g.ny), k = (int)(row / g.ny);
+    int ih, j, k;
+    tpb_ijk(t, nxh, g.ny, ih, j, k);
     int i = 2 * ih + ((col + j + k) & 1);
     if (i >= g.nx) return;
     rbgs_cell<NS, PROLONG>(a, b, x, g, i, j, k, zero_guess != 0, xc, cnx, cny, omega);
@@ -519,18 +514,17 @@ __global__ void __launch_bounds__(128) restrict_kernel(const double* __restrict_
                                                        double* __restrict__ bc) {
     long long C = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (C >= cg.n) return;
-    int I = (int)(C % cg.nx);
-    long long t = C / cg.nx;
-    bc[C] = restrict_cell<NS>(a, b, x, f, I, (int)(t % cg.ny), (int)(t / cg.ny));
+    int I, Jc, Kc;
+    tpb_ijk(C, cg.nx, cg.ny, I, Jc, Kc);
+    bc[C] = restrict_cell<NS>(a, b, x, f, I, Jc, Kc);
 }
 
 __global__ void __launch_bounds__(256) prolong_add_kernel(const double* __restrict__ xc, LevGeom f, LevGeom cg,
                                                           double omega, double* __restrict__ x) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= f.n) return;
-    int i = (int)(c % f.nx);
-    long long t = c / f.nx;
-    int j = (int)(t % f.ny), k = (int)(t / f.ny);
+    int i, j, k;
+    tpb_ijk(c, f.nx, f.ny, i, j, k);
     long long C = (i >> (f.cx - 1)) + (long long)cg.nx * ((j >> (f.cy - 1)) + (long long)cg.ny * (k >> (f.cz - 1)));
     x[c] += omega * xc[C];
 }
@@ -541,9 +535,8 @@ __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict_
                                                        const double* __restrict__ x, LevGeom g, double* __restrict__ r) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.n) return;
-    int i = (int)(c % g.nx);
-    long long t = c / g.nx;
-    int j = (int)(t % g.ny), k = (int)(t / g.ny);
+    int i, j, k;
+    tpb_ijk(c, g.nx, g.ny, i, j, k);
     double acc = b[c] - a[c] * x[c];
 #pragma unroll
     for (int s = 1; s < NS; s++) {
@@ -587,9 +580,8 @@ __device__ __forceinline__ void cyc_sweep(const TailLevel& L, bool zero_guess, c
     const long long total = (long long)g.ny * g.nz * nxh;
     for (int col = 0; col < 2; col++) {
         for (long long t = tid; t < total; t += nth) {
-            int ih = (int)(t % nxh);
-            long long row = t / nxh;
-            int j = (int)(row % g.ny), k = (int)(row / g.ny);
+            int ih, j, k;
+            tpb_ijk(t, nxh, g.ny, ih, j, k);
             int i = 2 * ih + ((col + j + k) & 1);
             if (i < g.nx) {
                 if (PROLONG && col == 0)
@@ -610,9 +602,9 @@ __device__ __forceinline__ void cyc_down(const TailArgs& A, int l0, int l1, long
         for (int s = 0; s < A.pre; s++) cyc_sweep<NS, false>(L, s == 0, nullptr, 0, 0, 0.0, tid, nth, bar);
         const TailLevel& Cc = A.lev[l + 1];
         for (long long C = tid; C < Cc.g.n; C += nth) {
-            int I = (int)(C % Cc.g.nx);
-            long long t = C / Cc.g.nx;
-            Cc.b[C] = restrict_cell<NS>(L.a, L.b, L.x, L.g, I, (int)(t % Cc.g.ny), (int)(t / Cc.g.ny));
+            int I, Jc, Kc;
+            tpb_ijk(C, Cc.g.nx, Cc.g.ny, I, Jc, Kc);
+            Cc.b[C] = restrict_cell<NS>(L.a, L.b, L.x, L.g, I, Jc, Kc);
         }
         bar();
     }
@@ -636,9 +628,8 @@ __device__ __forceinline__ void cyc_up(const TailArgs& A, int l1, int l0, long l
             for (int s = 1; s < A.post; s++) cyc_sweep<NS, false>(L, false, nullptr, 0, 0, 0.0, tid, nth, bar);
         } else {
             for (long long c = tid; c < f.n; c += nth) {
-                int i = (int)(c % f.nx);
-                long long t = c / f.nx;
-                int j = (int)(t % f.ny), k = (int)(t / f.ny);
+                int i, j, k;
+                tpb_ijk(c, f.nx, f.ny, i, j, k);
                 long long C = (i >> (f.cx - 1)) + (long long)Cc.g.nx * ((j >> (f.cy - 1)) + (long long)Cc.g.ny * (k >> (f.cz - 1)));
                 L.x[c] += A.omega * Cc.x[C];
             }
@@ -686,9 +677,8 @@ __global__ void __launch_bounds__(256) a00_sub_kernel(const double* __restrict__
     const long long n = g.n;
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    int i = (int)(c % g.nx);
-    long long t = c / g.nx;
-    int j = (int)(t % g.ny), k = (int)(t / g.ny);
+    int i, j, k;
+    tpb_ijk(c, g.nx, g.ny, i, j, k);
     double acc = 0.0;
 #pragma unroll
     for (int s = 0; s < 2 * DIM + 1; s++) {
@@ -707,9 +697,8 @@ __global__ void __launch_bounds__(128) ilu_setup_kernel(const double* __restrict
     const int nxh = (nx + 1) >> 1;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)ny * nz * nxh) return;
-    int ih = (int)(t % nxh);
-    long long row = t / nxh;
-    int j = (int)(row % ny), k = (int)(row / ny);
+    int ih, j, k;
+    tpb_ijk(t, nxh, ny, ih, j, k);
     int i = 2 * ih + ((col + j + k) & 1);
     if (i >= nx) return;
     long long c = i + (long long)nx * (j + (long long)ny * k);
@@ -760,9 +749,8 @@ __global__ void __launch_bounds__(128) ilu_half_kernel(const double* __restrict_
     const int nxh = (nx + 1) >> 1;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)ny * nz * nxh) return;
-    int ih = (int)(t % nxh);
-    long long row = t / nxh;
-    int j = (int)(row % ny), k = (int)(row / ny);
+    int ih, j, k;
+    tpb_ijk(t, nxh, ny, ih, j, k);
     int i = 2 * ih + ((col + j + k) & 1);
     if (i >= nx) return;
     long long c = i + (long long)nx * (j + (long long)ny * k);

@@ -18,10 +18,8 @@ __global__ void __launch_bounds__(256) spmv_kernel(const double* __restrict__ J,
     long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n) return;
     const int nx = g.nx, ny = g.ny, np = g.np;
-    int i = (int)(cell % nx);
-    long long t = cell / nx;
-    int j = (int)(t % ny);
-    int k = (int)(t / ny);
+    int i, j, k;
+    tpb_ijk(cell, nx, ny, i, j, k);
 
     double acc[NF];
 #pragma unroll
