@@ -1029,6 +1029,7 @@ static void stage2_setup(tpc_handle_s* h, const double* J) {
  * mode 0: z = Dinv r                       (red, forward)
  * mode 1: z = Dinv (r - sum A z[nb])       (black, forward)
  * mode 2: z = z - Dinv sum A z[nb]         (red, backward) */
+/* the triangular solves read fp32-rounded coefficients (the CUDA path stores the factor in fp32), fp64 arithmetic */
 static void stage2_half(const tpc_handle_s* h, const double* J, const double* r, double* z, int col, int mode) {
     const cgrid* g = &h->g;
     const int nf = h->nf, ns = g->ns, nx = g->nx, ny = g->ny, nz = g->nz;
@@ -1043,14 +1044,14 @@ static void stage2_half(const tpc_handle_s* h, const double* J, const double* r,
                 long nb = nbr(nx, ny, nz, i, j, k, s);
                 if (nb < 0) continue;
                 for (int a = 0; a < nf; a++)
-                    for (int q = 0; q < nf; q++) t[a] += Jat(J, n, nf, s, a, q, c) * z[(long)q * n + nb];
+                    for (int q = 0; q < nf; q++) t[a] += (double)(float)Jat(J, n, nf, s, a, q, c) * z[(long)q * n + nb];
             }
         }
         double v[MAXF];
         for (int a = 0; a < nf; a++) v[a] = mode == 2 ? t[a] : r[(long)a * n + c] - t[a];
         for (int a = 0; a < nf; a++) {
             double acc = 0.0;
-            for (int q = 0; q < nf; q++) acc += h->Dinv[(long)(a * nf + q) * n + c] * v[q];
+            for (int q = 0; q < nf; q++) acc += (double)(float)h->Dinv[(long)(a * nf + q) * n + c] * v[q];
             if (mode == 2)
                 z[(long)a * n + c] -= acc;
             else

@@ -52,6 +52,7 @@ struct PcState {
     double* AT = nullptr;
     MgHier mg_p, mg_T;
     double* Dinv = nullptr;
+    float *Dc = nullptr, *Lc = nullptr;   // colour-separated fp32 copies of the ILU factor (tpb_pc.cu: ilu_setup_kernel)
     double *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
     double* strength = nullptr;  // 3 doubles (device)
     bool ready = false;
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(256) a00_sub_kernel(const double* __restrict__
 // ---- K8: red-black block ILU(0) --------------------------------------------------------------------
 template <int NF, int DIM>
 __global__ void __launch_bounds__(128) ilu_setup_kernel(const double* __restrict__ J, Geom g, int col, int ilu,
-                                                        double* Dinv) {
+                                                        double* Dinv, float* __restrict__ Dc, float* __restrict__ Lc) {
     const long long n = g.n;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
     const int nxh = (nx + 1) >> 1;
@@ -736,19 +737,34 @@ __global__ void __launch_bounds__(128) ilu_setup_kernel(const double* __restrict
     inv_block(NF, D, Di);
 #pragma unroll
     for (int e = 0; e < NF * NF; e++) Dinv[(long long)e * n + c] = Di[e];
+    if (Lc) {
+        // what the triangular solves read: colour-separated (cells of one colour contiguous, index t) fp32 copies of
+        // the inverted diagonal blocks and of the off-diagonal blocks - a colour pass then uses every byte of
+        // every sector it touches and moves half the bytes
+        const long long nth = (long long)ny * nz * nxh;
+#pragma unroll
+        for (int e = 0; e < NF * NF; e++) Dc[((long long)col * NF * NF + e) * nth + t] = (float)Di[e];
+#pragma unroll
+        for (int s = 1; s < 2 * DIM + 1; s++)
+#pragma unroll
+            for (int e = 0; e < NF * NF; e++)
+                Lc[(((long long)col * 2 * DIM + (s - 1)) * NF * NF + e) * nth + t] = (float)J[((long long)s * NF * NF + e) * n + c];
+    }
 }
 
 // mode 0: z = Dinv r (red, forward); 1: z = Dinv (r - sum A z[nb]) (black, forward);
-// mode 2: z -= Dinv sum A z[nb] (red, backward)
+// mode 2: z -= Dinv sum A z[nb] (red, backward).  Coefficients come from the colour-separated fp32 copies
+// (the factor is a preconditioner: fp32 storage, fp64 arithmetic); vectors stay fp64 in natural order.
 template <int NF, int DIM>
-__global__ void __launch_bounds__(128) ilu_half_kernel(const double* __restrict__ J, const double* __restrict__ Dinv,
+__global__ void __launch_bounds__(128) ilu_half_kernel(const float* __restrict__ Lc, const float* __restrict__ Dc,
                                                        const double* __restrict__ r, double* z, Geom g, int col,
                                                        int mode) {
     const long long n = g.n;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
     const int nxh = (nx + 1) >> 1;
+    const long long nth = (long long)ny * nz * nxh;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)ny * nz * nxh) return;
+    if (t >= nth) return;
     int ih, j, k;
     tpb_ijk(t, nxh, ny, ih, j, k);
     int i = 2 * ih + ((col + j + k) & 1);
@@ -760,25 +776,30 @@ __global__ void __launch_bounds__(128) ilu_half_kernel(const double* __restrict_
     if (mode != 0) {
 #pragma unroll
         for (int s = 1; s < 2 * DIM + 1; s++) {
-            long long nb = nbr_cell(nx, ny, nz, i, j, k, c, s);
-            if (nb < 0) continue;
+            bool ex;
+            long long nb = nbr_clamped(nx, ny, nz, i, j, k, c, s, ex);
             double zn[NF];
 #pragma unroll
             for (int q = 0; q < NF; q++) zn[q] = z[(long long)q * n + nb];
+            const float* L = Lc + (((long long)col * 2 * DIM + (s - 1)) * NF * NF) * nth + t;
 #pragma unroll
-            for (int a = 0; a < NF; a++)
+            for (int a = 0; a < NF; a++) {
+                double p = 0.0;
 #pragma unroll
-                for (int q = 0; q < NF; q++) tt[a] += JAT(s, a, q, c) * zn[q];
+                for (int q = 0; q < NF; q++) p += (double)L[(long long)(a * NF + q) * nth] * zn[q];
+                tt[a] += ex ? p : 0.0;
+            }
         }
     }
     double v[NF];
 #pragma unroll
     for (int a = 0; a < NF; a++) v[a] = mode == 2 ? tt[a] : r[(long long)a * n + c] - tt[a];
+    const float* Dp = Dc + ((long long)col * NF * NF) * nth + t;
 #pragma unroll
     for (int a = 0; a < NF; a++) {
         double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < NF; q++) acc += Dinv[(long long)(a * NF + q) * n + c] * v[q];
+        for (int q = 0; q < NF; q++) acc += (double)Dp[(long long)(a * NF + q) * nth] * v[q];
         if (mode == 2)
             z[(long long)a * n + c] -= acc;
         else
@@ -1045,9 +1066,14 @@ void stage2_setup_t(tpb_handle_s* h, const double* J) {
     if (h->opts.stage2 == TPB_S2_NONE) return;
     if (!pc->Dinv) pc->Dinv = tpb_dalloc<double>((size_t)NF * NF * n);
     long long threads = (long long)h->g.ny * h->g.nz * ((h->g.nx + 1) >> 1);
+    const bool ilu = h->opts.stage2 == TPB_S2_ILU0;
+    if (ilu && !pc->Lc) {
+        pc->Dc = tpb_dalloc<float>((size_t)2 * NF * NF * threads);
+        pc->Lc = tpb_dalloc<float>((size_t)2 * 2 * DIM * NF * NF * threads);
+    }
     for (int col = 0; col < 2; col++) {
-        ilu_setup_kernel<NF, DIM><<<nblk(threads, 128), 128, 0, h->stream>>>(J, h->g, col,
-                                                                            h->opts.stage2 == TPB_S2_ILU0 ? 1 : 0, pc->Dinv);
+        ilu_setup_kernel<NF, DIM><<<nblk(threads, 128), 128, 0, h->stream>>>(J, h->g, col, ilu ? 1 : 0, pc->Dinv,
+                                                                            ilu ? pc->Dc : nullptr, ilu ? pc->Lc : nullptr);
         h->launches++;
     }
 }
@@ -1064,7 +1090,7 @@ void stage2_apply_t(tpb_handle_s* h, const double* r, double* z) {
     long long threads = (long long)h->g.ny * h->g.nz * ((h->g.nx + 1) >> 1);
     const int seq[3][2] = {{0, 0}, {1, 1}, {0, 2}};
     for (int q = 0; q < 3; q++) {
-        ilu_half_kernel<NF, DIM><<<nblk(threads, 128), 128, 0, h->stream>>>(pc->J, pc->Dinv, r, z, h->g, seq[q][0], seq[q][1]);
+        ilu_half_kernel<NF, DIM><<<nblk(threads, 128), 128, 0, h->stream>>>(pc->Lc, pc->Dc, r, z, h->g, seq[q][0], seq[q][1]);
         h->launches++;
     }
 }
@@ -1155,6 +1181,8 @@ void tpb_pc_free(tpb_handle_s* h) {
     tpb_dfree(pc->A00);
     tpb_dfree(pc->AT);
     tpb_dfree(pc->Dinv);
+    tpb_dfree(pc->Dc);
+    tpb_dfree(pc->Lc);
     tpb_dfree(pc->t0);
     tpb_dfree(pc->t1);
     tpb_dfree(pc->t2);
