@@ -112,6 +112,11 @@ int tpb_create(const tpb_grid* grid, int nphase, const tpb_params* prm, int devi
         d.mu_o_pref = 1e-3 * pow(10.0, -0.8021 * prm->API + 23.8765);                   // :52-57
         d.mu_o_exp = 0.31458 * prm->API - 9.21592;
         TPB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        TPB_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        TPB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        TPB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        h->src_index = tpb_dalloc<int>(g.n);
+        TPB_CUDA(cudaMemsetAsync(h->src_index, 0xff, g.n * sizeof(int), h->stream));
         for (int f = 0; f < 5; f++) {
             h->fld[f] = tpb_dalloc<double>(g.n);
             h->fld_lo[f] = tpb_dalloc<double>(g.np);
@@ -161,6 +166,11 @@ int tpb_destroy(tpb_handle h) {
     tpb_dfree(h->src_cell);
     tpb_dfree(h->src_off);
     tpb_dfree(h->src_ent);
+    tpb_dfree(h->src_index);
+    tpb_dfree(h->src_acc);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     tpb_dfree(h->red_partial);
     tpb_dfree(h->red_counter);
     tpb_dfree(h->red_out);
@@ -207,6 +217,9 @@ int tpb_set_sources(tpb_handle h, int n, const tpb_source* src) {
     tpb_dfree(h->src_cell);
     tpb_dfree(h->src_off);
     tpb_dfree(h->src_ent);
+    tpb_dfree(h->src_acc);
+    h->src_acc = nullptr;
+    TPB_CUDA(cudaMemsetAsync(h->src_index, 0xff, h->g.n * sizeof(int), h->stream));
     h->src_cell = nullptr;
     h->src_off = nullptr;
     h->src_ent = nullptr;
@@ -235,6 +248,12 @@ int tpb_set_sources(tpb_handle h, int n, const tpb_source* src) {
         TPB_CUDA(cudaMemcpy(h->src_cell, cells.data(), cells.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
         TPB_CUDA(cudaMemcpy(h->src_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
         TPB_CUDA(cudaMemcpy(h->src_ent, ent.data(), (size_t)n * sizeof(tpb_source), cudaMemcpyHostToDevice));
+        h->src_acc = tpb_dalloc<double>(cells.size() * (size_t)(h->nf + h->nf * h->nf));
+        TPB_CUDA(cudaMemsetAsync(h->src_acc, 0, cells.size() * (size_t)(h->nf + h->nf * h->nf) * sizeof(double), h->stream));
+        std::vector<int> idx(h->g.n, -1);
+        for (size_t q = 0; q < cells.size(); q++) idx[cells[q]] = (int)q;
+        TPB_CUDA(cudaMemcpyAsync(h->src_index, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        TPB_CUDA(cudaStreamSynchronize(h->stream));
     }
     TPB_CATCH(h)
 }

@@ -231,8 +231,10 @@ struct Trans {
 
 template <int NF, int DIM, bool JAC, bool HALO, int MINB>
 __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, const double* __restrict__ u_old,
-                                                             const double* __restrict__ scr, Trans tr, double idt,
-                                                             Geom g, DevParams P, double* __restrict__ F,
+                                                             const double* __restrict__ scr, Trans tr,
+                                                             const int* __restrict__ src_index,
+                                                             const double* __restrict__ src_acc, double idt, Geom g,
+                                                             DevParams P, double* __restrict__ F,
                                                              double* __restrict__ J) {
     const long long n = g.n;
     long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,6 +375,20 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
         }
     }
 
+    if (src_index) {   // wells / heaters in this cell (sources_kernel)
+        const int si = src_index[cell];
+        if (si >= 0) {
+            const double* o = src_acc + (long long)si * (NF + NF * NF);
+#pragma unroll
+            for (int r = 0; r < NF; r++) {
+                R[r] += o[r];
+                if (JAC) {
+#pragma unroll
+                    for (int c = 0; c < NF; c++) D[r][c] += o[NF + r * NF + c];
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int r = 0; r < NF; r++) F[(long long)r * n + cell] = R[r];
     if (JAC) {
@@ -412,11 +428,14 @@ __device__ __forceinline__ Dual<NF> well_rate(const tpb_source& s, double wi, co
     return rate;
 }
 
+// One thread per source cell; runs on the handle's side stream concurrently with props_kernel and leaves the
+// residual / diagonal-block contributions of the cell's wells and heaters in acc_out[t][NF + NF*NF], which
+// assemble_kernel adds to the row it is writing anyway (src_index[cell] = t, or -1).
 template <int NF, bool JAC>
 __global__ void sources_kernel(int ncells, const int64_t* __restrict__ cells, const int* __restrict__ off,
                                const tpb_source* __restrict__ ent, const double* __restrict__ u,
                                const double* __restrict__ Kx, const double* __restrict__ Ky, long long n, DevParams P,
-                               double* __restrict__ F, double* __restrict__ J) {
+                               double* __restrict__ acc_out) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncells) return;
     long long cell = cells[t];
@@ -500,12 +519,13 @@ __global__ void sources_kernel(int ncells, const int64_t* __restrict__ cells, co
             }
         }
     }
+    double* o = acc_out + (long long)t * (NF + NF * NF);
 #pragma unroll
     for (int r = 0; r < NF; r++) {
-        F[(long long)r * n + cell] += acc[r].v;
+        o[r] = acc[r].v;
         if (JAC) {
 #pragma unroll
-            for (int c = 0; c < NF; c++) J[((long long)r * NF + c) * n + cell] += acc[r].d[c];
+            for (int c = 0; c < NF; c++) o[NF + r * NF + c] = acc[r].d[c];
         }
     }
 }
@@ -522,7 +542,7 @@ void launch_k(tpb_handle_s* h, const Fields<NF>& fl, const double* u_old, double
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
     static int variant = getenv("TPB_ASM_MINB") ? atoi(getenv("TPB_ASM_MINB")) : 4;
 #define TPB_ASM(JAC, MINB) \
-    assemble_kernel<NF, DIM, JAC, HALO, MINB><<<blocks, threads, 0, h->stream>>>(fl, u_old, h->scr, tr, 1.0 / dt, h->g, h->dp, F, J)
+    assemble_kernel<NF, DIM, JAC, HALO, MINB><<<blocks, threads, 0, h->stream>>>(fl, u_old, h->scr, tr, h->nsrc_cells > 0 ? h->src_index : nullptr, h->src_acc, 1.0 / dt, h->g, h->dp, F, J)
     if (J) {
         if (variant == 3)
             TPB_ASM(true, 3);
@@ -571,24 +591,29 @@ void launch_t(tpb_handle_s* h, const double* u, const double* u_old, double dt, 
         h->launches++;
         h->trans_dirty = false;
     }
+    if (h->nsrc_cells > 0) {
+        // fork: the few source cells are evaluated on the side stream while the property pre-pass runs
+        TPB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        TPB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        const unsigned sb = (unsigned)((h->nsrc_cells + 127) / 128);
+        if (J)
+            sources_kernel<NF, true><<<sb, 128, 0, h->stream2>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
+                                                                h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, h->src_acc);
+        else
+            sources_kernel<NF, false><<<sb, 128, 0, h->stream2>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
+                                                                 h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, h->src_acc);
+        h->launches++;
+        TPB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+    }
     props_kernel<NF><<<(unsigned)((ne + 255) / 256), 256, 0, h->stream>>>(fl, n, np, h->g.has_lo, h->g.has_hi, h->dp,
                                                                          h->scr);
     h->launches++;
+    if (h->nsrc_cells > 0) TPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     if (h->g.has_lo || h->g.has_hi)
         launch_k<NF, DIM, true>(h, fl, u_old, dt, F, J);
     else
         launch_k<NF, DIM, false>(h, fl, u_old, dt, F, J);
     h->launches++;
-    if (h->nsrc_cells > 0) {
-        const unsigned sb = (unsigned)((h->nsrc_cells + 127) / 128);
-        if (J)
-            sources_kernel<NF, true><<<sb, 128, 0, h->stream>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
-                                                               h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, F, J);
-        else
-            sources_kernel<NF, false><<<sb, 128, 0, h->stream>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
-                                                                h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, F, J);
-        h->launches++;
-    }
     TPB_CUDA(cudaGetLastError());
 }
 

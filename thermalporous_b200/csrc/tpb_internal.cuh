@@ -202,8 +202,9 @@ __device__ __forceinline__ double oil_rho_v(const DevParams& P, double p, double
 // 1/oil_mu, oil_mu = 1e-3 * 10^{A1 API + A2} * Tf^{A3 API + A4}, Tf = 1.8 (T - 273.15) + 32   (:48-57)
 __device__ __forceinline__ void oil_imu_d(const DevParams& P, double T, double& im, double& im_T) {
     double Tf = 1.8 * (T - 273.15) + 32.0;
-    double mu = P.mu_o_pref * pow(Tf, P.mu_o_exp);
-    im = 1.0 / mu;
+    // Tf^e as exp(e log Tf): |e log Tf| < 40, so the relative error is < 1e-14 (parity tolerance 1e-12) at half
+    // the cost of the correctly rounded pow()
+    im = exp(-P.mu_o_exp * log(Tf)) / P.mu_o_pref;
     im_T = -im * P.mu_o_exp * 1.8 / Tf;  // d(1/mu)/dT = -(1/mu) * exp * Tf'/Tf
 }
 // water_rho: Trangenstein/Kell (:69-82), Tc = T - 272.15
@@ -274,6 +275,10 @@ struct tpb_handle_s {
     int64_t* src_cell = nullptr;  // unique cells
     int* src_off = nullptr;       // CSR offsets into src_ent
     tpb_source* src_ent = nullptr;
+    int* src_index = nullptr;     // per cell: index into src_cell / src_acc, or -1
+    double* src_acc = nullptr;    // nsrc_cells * (nf + nf*nf) contributions of the current assembly
+    cudaStream_t stream2 = nullptr;   // side stream (source cells run beside the property pre-pass)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // reductions
     double* red_partial = nullptr;   // per-block partials
