@@ -107,3 +107,17 @@ def test_unsupported_option_set_is_loud():
     case = CS.WellCase(prm, geo, well_case="test0", constant_rate=True)
     with pytest.raises(O.UnsupportedOption):
         TwoPhase(geo, case, prm, solver_parameters="pc_lu", verbosity=False)
+
+
+def test_c4_two_phase_homogeneous_heaters():
+    """tests_twophase/test3D_homo_heater.py (BASELINE config 4) at N = 20: 42 heater points, 3 steps of one day."""
+    from tools.run_c4 import build
+    model = build(20, steps=3)
+    res = check(model, 2, "pc_cptr")
+    assert len(res.dt_vec) == 3
+    p, T, S = model.fields()
+    assert prm_close(T.max(), 373.15) and T.min() >= 288.7
+
+
+def prm_close(tmax, t_inj):
+    return 300.0 < tmax <= t_inj + 1e-6
