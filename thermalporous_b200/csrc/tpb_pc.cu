@@ -57,10 +57,10 @@ struct PcState {
     double* strength = nullptr;  // 3 doubles (device)
     bool ready = false;
     // the whole PC apply (~100 small dependent kernels) replayed as one CUDA graph on fixed in/out buffers
-    cudaGraphExec_t gexec = nullptr;
+    cudaGraphExec_t gexec = nullptr, gexec2 = nullptr;
     double *gx = nullptr, *gy = nullptr;
-    int64_t graph_nodes = 0;
-    bool graph_ok = false;
+    int64_t graph_nodes = 0, graph_nodes2 = 0;
+    bool graph_ok = false, split = false;
 };
 
 namespace {
@@ -1133,11 +1133,24 @@ void pc_setup_t(tpb_handle_s* h, const double* J, const double* u, double dt) {
     stage2_setup_t<NF, DIM>(h, J);
 }
 
+// part 0: the whole application; part 1: stage 1 only; part 2: what follows the residual SpMV (t0 holds J y).
+// The split exists for slabs with neighbours: the SpMV needs an NCCL halo exchange, which stays outside the
+// two CUDA graphs that replay parts 1 and 2.
 template <int NF, int DIM>
-void pc_apply_t(tpb_handle_s* h, const double* x, double* y) {
+void pc_apply_t(tpb_handle_s* h, const double* x, double* y, int part = 0) {
     PcState* pc = h->pc;
     const tpb_solver_opts& o = h->opts;
     const size_t nd = (size_t)NF * h->g.n;
+    if (part == 1) {
+        stage1_apply_t<NF, DIM>(h, x, y);
+        return;
+    }
+    if (part == 2) {
+        tpb_axpby(h, nd, 1.0, x, -1.0, pc->t0);  // t0 = x - J y
+        stage2_apply_t<NF, DIM>(h, pc->t0, pc->t1);
+        tpb_axpy(h, nd, 1.0, pc->t1, y);
+        return;
+    }
     if (o.stage1 == TPB_S1_NONE && o.stage2 == TPB_S2_NONE) {
         tpb_copy(h, nd, x, y);
         return;
@@ -1189,6 +1202,7 @@ void tpb_pc_free(tpb_handle_s* h) {
     tpb_dfree(pc->t3);
     tpb_dfree(pc->strength);
     if (pc->gexec) cudaGraphExecDestroy(pc->gexec);
+    if (pc->gexec2) cudaGraphExecDestroy(pc->gexec2);
     tpb_dfree(pc->gx);
     tpb_dfree(pc->gy);
     delete pc;
@@ -1210,43 +1224,59 @@ void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double
     DISPATCH(pc_setup_t, h, J, u, dt);
     TPB_CUDA(cudaGetLastError());
     h->pc->ready = true;
-    // Capture one application into a CUDA graph (single-rank slabs only: the multi-rank apply contains NCCL
-    // halo exchanges).  The Krylov loop applies the PC 20-30 times per set-up; replaying removes the host-side
-    // launch cost of its ~100 small kernels.  TPB_GRAPH=0 disables it.
+    // Capture one application into a CUDA graph: the Krylov loop applies the PC 20-30 times per set-up and
+    // replaying removes the host-side launch cost of its ~100 small kernels.  Slabs with neighbours need an
+    // NCCL halo exchange for the residual SpMV of the multiplicative composite, so there the application is
+    // two graphs (stage 1 | stage 2) around that SpMV.  TPB_GRAPH=0 disables it.
     PcState* pc = h->pc;
     pc->graph_ok = false;
+    pc->split = false;
     static const bool want = !(getenv("TPB_GRAPH") && atoi(getenv("TPB_GRAPH")) == 0);
-    const bool any = h->opts.stage1 != TPB_S1_NONE || h->opts.stage2 != TPB_S2_NONE;
-    if (want && any && !(h->g.has_lo || h->g.has_hi)) {
+    const tpb_solver_opts& o = h->opts;
+    const bool any = o.stage1 != TPB_S1_NONE || o.stage2 != TPB_S2_NONE;
+    const bool halo = h->g.has_lo || h->g.has_hi;
+    const bool two_stage = o.stage1 != TPB_S1_NONE && o.stage2 != TPB_S2_NONE && o.stage1 != TPB_S1_FIELDSPLIT;
+    if (want && any) {
         const size_t nd = (size_t)h->nf * h->g.n;
         if (!pc->gx) pc->gx = tpb_dalloc<double>(nd);
         if (!pc->gy) pc->gy = tpb_dalloc<double>(nd);
-        cudaGraph_t graph = nullptr;
-        const int64_t l0 = h->launches;
-        TPB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        try {
-            DISPATCH(pc_apply_t, h, pc->gx, pc->gy);
-        } catch (...) {
-            cudaStreamEndCapture(h->stream, &graph);
-            if (graph) cudaGraphDestroy(graph);
-            throw;
-        }
-        TPB_CUDA(cudaStreamEndCapture(h->stream, &graph));
-        pc->graph_nodes = h->launches - l0;
-        h->launches = l0;
-        bool updated = false;
-        if (pc->gexec) {
-            cudaGraphExecUpdateResultInfo info;
-            updated = cudaGraphExecUpdate(pc->gexec, graph, &info) == cudaSuccess;
-            if (!updated) {
-                cudaGetLastError();
-                cudaGraphExecDestroy(pc->gexec);
-                pc->gexec = nullptr;
+        pc->split = halo && two_stage;
+        auto capture = [&](int part, cudaGraphExec_t& gexec, int64_t& nodes) {
+            cudaGraph_t graph = nullptr;
+            const int64_t l0 = h->launches;
+            TPB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            try {
+                DISPATCH(pc_apply_t, h, pc->gx, pc->gy, part);
+            } catch (...) {
+                cudaStreamEndCapture(h->stream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
             }
+            TPB_CUDA(cudaStreamEndCapture(h->stream, &graph));
+            nodes = h->launches - l0;
+            h->launches = l0;
+            bool updated = false;
+            if (gexec) {
+                cudaGraphExecUpdateResultInfo info;
+                updated = cudaGraphExecUpdate(gexec, graph, &info) == cudaSuccess;
+                if (!updated) {
+                    cudaGetLastError();
+                    cudaGraphExecDestroy(gexec);
+                    gexec = nullptr;
+                }
+            }
+            if (!updated) TPB_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+            cudaGraphDestroy(graph);
+        };
+        if (pc->split) {
+            capture(1, pc->gexec, pc->graph_nodes);
+            capture(2, pc->gexec2, pc->graph_nodes2);
+            pc->graph_ok = true;
+        } else if (!halo || !two_stage) {
+            // single slab, or an application without the residual SpMV (no NCCL inside)
+            capture(0, pc->gexec, pc->graph_nodes);
+            pc->graph_ok = true;
         }
-        if (!updated) TPB_CUDA(cudaGraphInstantiate(&pc->gexec, graph, 0));
-        cudaGraphDestroy(graph);
-        pc->graph_ok = true;
     }
 }
 
@@ -1257,8 +1287,13 @@ void tpb_pc_apply_impl(tpb_handle_s* h, const double* x, double* y) {
         const size_t nd = (size_t)h->nf * h->g.n;
         TPB_CUDA(cudaMemcpyAsync(pc->gx, x, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         TPB_CUDA(cudaGraphLaunch(pc->gexec, h->stream));
-        TPB_CUDA(cudaMemcpyAsync(y, pc->gy, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         h->launches += pc->graph_nodes;
+        if (pc->split) {
+            tpb_launch_spmv(h, pc->J, pc->gy, pc->t0);   // with its NCCL halo exchange
+            TPB_CUDA(cudaGraphLaunch(pc->gexec2, h->stream));
+            h->launches += pc->graph_nodes2;
+        }
+        TPB_CUDA(cudaMemcpyAsync(y, pc->gy, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         return;
     }
     DISPATCH(pc_apply_t, h, x, y);
