@@ -32,6 +32,13 @@ COMBOS = [
     (2, 3, (4, 6, 40), dict(stage1=cport.S1_NONE, stage2=cport.S2_ILU0)),
     (2, 3, (4, 6, 10), dict(stage1=cport.S1_CPR, stage2=cport.S2_BJACOBI)),
     (2, 3, (20, 24, 40), dict(stage1=cport.S1_CPTR, decoup=1, mg_pre=2, mg_post=2, mg_cycles=2)),
+    # degenerate shapes: single columns / rows / cells (odd sizes exercise the ragged last aggregate)
+    (2, 3, (9, 1, 1), dict(stage1=cport.S1_CPTR, decoup=1)),
+    (2, 3, (1, 1, 7), dict(stage1=cport.S1_CPR, decoup=2)),
+    (1, 3, (1, 5, 1), dict(stage1=cport.S1_CPR, decoup=1)),
+    (2, 2, (1, 1, 1), dict(stage1=cport.S1_CPTR)),
+    (2, 3, (3, 3, 3), dict(stage1=cport.S1_CPTR, mg_pre=1, mg_post=0, mg_coarse_sweeps=1)),
+    (2, 3, (17, 19, 23), dict(stage1=cport.S1_CPTR, decoup=2, mg_semi_theta=0.0, mg_full_below=100)),
 ]
 TOL = 1e-10
 
@@ -104,6 +111,33 @@ def test_ksp_matches_cpu_restatement(nphase, dim, shape, opts, ksp_type):
     res = np.linalg.norm(orc.spmv(Jh, pb.grid, xg.cpu().numpy()) - Fh) / np.linalg.norm(Fh)
     assert res < 5 * rtol
     assert rel_err_rows(xg.cpu().numpy(), xc) < 1e4 * rtol
+    g.close()
+    c.close()
+
+
+def test_zero_permeability_cells_and_sources_in_the_solver():
+    """cells cut off from their neighbours (K = 0: pure accumulation rows) and active wells / heaters:
+    PC components, Krylov counts and the Newton update agree with the CPU restatement."""
+    pb, u, uo = random_problem(3, 2, (7, 9, 11), seed=9, spread=0.02, nsrc=5)
+    rng = np.random.default_rng(2)
+    dead = rng.random(pb.grid.n) < 0.07
+    for K in (pb.Kx, pb.Ky, pb.Kz):
+        K[dead] = 0.0
+    g = engine_from_problem(pb)
+    c = cport.engine_from_problem(pb)
+    for e in (g, c):
+        e.set_solver_opts(stage1=cport.S1_CPTR, decoup=1, ksp_rtol=1e-9)
+    F, J = g.assemble(u, uo, 2000.0)
+    Fc, Jc = c.assemble(u, uo, 2000.0)
+    assert rel_err_rows(F.cpu().numpy(), Fc) < 1e-12 and rel_err_rows(J.cpu().numpy(), Jc) < 1e-12
+    g.pc_setup(J, u, 2000.0)
+    c.pc_setup(Jc, u, 2000.0)
+    x = rng.normal(size=(3, pb.grid.n))
+    assert rel_err_rows(g.pc_apply(x).cpu().numpy(), c.pc_apply(x)) < 1e-9
+    xg, its_g, reason_g, _ = g.ksp_solve(J, F)
+    xc, its_c, reason_c, _ = c.ksp_solve(Jc, Fc)
+    assert reason_g == reason_c == 2 and abs(its_g - its_c) <= 1
+    assert rel_err_rows(xg.cpu().numpy(), xc) < 1e-5
     g.close()
     c.close()
 
