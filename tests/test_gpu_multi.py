@@ -19,4 +19,4 @@ def test_two_slabs_reproduce_single_domain():
            "--master-port", "29531", os.path.join(ROOT, "tools", "mgpu_check.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("| OK") == 2
+    assert out.stdout.count("| OK") == 4      # two checks (kernels + Newton, model.solve()) on two ranks

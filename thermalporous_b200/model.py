@@ -175,19 +175,38 @@ class ThermalModel:
         self.maxdt, self.dt_init_fact, self.end, self.verbosity = maxdt, dt_init_fact, end, verbosity
         self.filename = filename
         geo, prm = self.geo, self.params
-        self.engine = Engine(geo.dim, geo.Nx, geo.Ny, getattr(geo, "Nz", 1), geo.Dx, geo.Dy,
-                             getattr(geo, "Dz", 1.0), self.nphase, prm, device=device)
+        # One process per GPU: under `torchrun` (torch.distributed initialised with the nccl backend) every rank
+        # owns one z-slab (y-slab in 2-D) of the geo, as every MPI rank owns a mesh partition in the reference
+        # (mesh.comm, singlephase.py:13); a single process owns the whole grid.
+        from .partition import Slab
+        self.rank, self.world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        self.slab = slab = Slab(geo, self.world, self.rank)
+        nxl, nyl, nzl = slab.local_dims()
+        self.engine = Engine(geo.dim, nxl, nyl, nzl, geo.Dx, geo.Dy, getattr(geo, "Dz", 1.0), self.nphase, prm,
+                             device=device, has_lo=slab.has_lo, has_hi=slab.has_hi)
         e = self.engine
-        e.set_field(L.TPB_PHI, geo.phi)
-        e.set_field(L.TPB_KX, geo.K_x)
-        e.set_field(L.TPB_KY, geo.K_y)
+        e.set_field(L.TPB_PHI, slab.take(geo.phi))
+        e.set_field(L.TPB_KX, slab.take(geo.K_x))
+        e.set_field(L.TPB_KY, slab.take(geo.K_y))
         if geo.dim == 3:
-            e.set_field(L.TPB_KZ, geo.K_z)
+            e.set_field(L.TPB_KZ, slab.take(geo.K_z))
         if self.nphase == 1:
-            e.set_field(L.TPB_KT, geo.kT)
-        e.set_sources(source_entries(self.case, prm, geo))
+            e.set_field(L.TPB_KT, slab.take(geo.kT))
+        e.set_sources(slab.localize_sources(source_entries(self.case, prm, geo)))
+        if self.world > 1:
+            import torch.distributed as dist
+            uid = [e.unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            e.comm_init(uid[0], self.rank, self.world)
+            e.exchange_static()
         e.set_solver_opts(**self.solver_opts)
-        self.initial_condition = self.init_IC_uniform()
+        self.initial_condition = slab.take(self.init_IC_uniform())      # this rank's part
         self.u = e.tensor(self.initial_condition)
         self.u_ = self.u.clone()
         self.total_nits = self.total_lits = 0
@@ -195,28 +214,32 @@ class ThermalModel:
         self.result = None
 
     def resultprint(self, *args):
-        if self.verbosity:
+        if self.verbosity and self.rank == 0:
             print(*args)
+
+    def _rank_suffix(self):
+        return "" if self.world == 1 else "_rank%dof%d" % (self.rank, self.world)
 
     def solve(self, max_steps=None):
         e = self.engine
         if self.checkpointing["load"]:                           # thermalmodel.py:87-91
             self.resultprint("Using as initial solution checkpoint " + self.checkpointing["loadname"])
-            self.u.copy_(e.tensor(load_checkpoint(self.checkpointing["loadname"], self.u.shape)))
+            self.u.copy_(e.tensor(load_checkpoint(self.checkpointing["loadname"] + self._rank_suffix(), self.u.shape)))
         else:
             self.u.copy_(e.tensor(self.initial_condition))
         self.u_.copy_(self.u)
         res = run_time_loop(lambda u, uo, dt: e.newton_solve(u, uo, dt), _TorchOps(e), self.u, self.u_,
                             end=self.end, maxdt=self.maxdt, small_dt_start=self.small_dt_start,
                             dt_init_fact=self.dt_init_fact, two_phase=self.nphase == 2, i_S=2,
-                            spe10=self.geo.name.startswith("SPE10"), verbose=self.verbosity, max_steps=max_steps)
+                            spe10=self.geo.name.startswith("SPE10"), verbose=self.verbosity and self.rank == 0,
+                            max_steps=max_steps)
         self.result = res
         self.total_nits, self.total_lits = res.total_nits, res.total_lits
         self.last_dt = res.dt_vec[-1] if res.dt_vec else None
         if self.checkpointing["save"]:                           # thermalmodel.py:361-364
-            save_checkpoint(self.checkpointing["savename"], self.u.detach().cpu().numpy())
+            save_checkpoint(self.checkpointing["savename"] + self._rank_suffix(), self.u.detach().cpu().numpy())
             self.resultprint("Saving checkpoint solution in " + self.checkpointing["savename"])
-        if self.verbosity and res.dt_vec:                       # thermalmodel.py:367-408
+        if self.verbosity and res.dt_vec and self.rank == 0:    # thermalmodel.py:367-408
             p = self.resultprint
             p("nits = ", res.nits_vec, ";")
             p("lits = ", res.lits_vec, ";")
@@ -235,7 +258,7 @@ class ThermalModel:
         return res
 
     def fields(self):
-        """converged fields as host arrays: (p, T[, S_o])."""
+        """converged fields of THIS rank's slab as host arrays: (p, T[, S_o]); cells self.slab.c0 .. c1 of the geo."""
         return tuple(self.u.detach().cpu().numpy())
 
 

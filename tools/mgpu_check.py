@@ -57,6 +57,33 @@ smin, smax = eng.field_minmax(ug, 2)
 ok = eF < 1e-12 and eJ < 1e-12 and ey < 1e-12 and st.reason > 0 and eu < 1e-8 and abs(smax - uc[2].max()) < 1e-8
 print("rank %d/%d: F %.1e J %.1e spmv %.1e | newton nits %d (cpu %d) lits %d (cpu %d) reason %d fields %.1e | %s"
       % (rank, world, eF, eJ, ey, st.nits, sc.nits, st.lits, sc.lits, st.reason, eu, "OK" if ok else "FAIL"), flush=True)
+eng.close()
+# the mirrored model class under torchrun: each rank owns a slab; same time loop as the single-domain CPU run
+from thermalporous_b200.model import TwoPhase, run_time_loop
+model = TwoPhase(geo, case, prm, end=0.002, maxdt=0.001, small_dt_start=True, dt_init_fact=2 ** -2,
+                 solver_parameters="pc_cptr", verbosity=False, device=local)
+res = model.solve()
+class NpOps:
+    def copy(self, d, s): d[...] = s
+    def minmax(self, u, f): return float(u[f].min()), float(u[f].max())
+    def clip(self, u, f, lo, hi): np.clip(u[f], lo, hi, out=u[f])
+# a Newton count at the tolerance edge steers the SPE10 dt heuristic, so the CPU run follows the dt sequence the
+# 2-rank run took (default tolerances on the GPU side, tight ones here -> agreement to the GPU run's accuracy)
+o2, _, _ = O.resolve("pc_cptr", 2)
+o2.update(snes_rtol=1e-11, snes_stol=1e-13)
+cpu.set_solver_opts(**o2)
+uc2 = u0.copy()
+class RC: pass
+rc = RC(); rc.nits_vec = []
+for dt in res.dt_vec:
+    st2 = cpu.newton_solve(uc2, uc2.copy(), dt)
+    rc.nits_vec.append(st2.nits)
+    np.clip(uc2[2], 0.0, 1.0, out=uc2[2])
+em = max(rel(model.fields()[f], slab.take(uc2)[f]) for f in range(3))
+ok2 = res.failed_solves == 0 and abs(res.t - 0.002 * 86400.0) < 1e-6 and em < 1e-6
+print("rank %d/%d: model.solve() %d steps nits %s (cpu %s) fields %.1e | %s" % (rank, world, len(res.dt_vec), res.nits_vec,
+      rc.nits_vec, em, "OK" if ok2 else "FAIL"), flush=True)
+ok = ok and ok2
 t = torch.tensor([1.0 if ok else 0.0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
-eng.close(); dist.destroy_process_group()
+dist.destroy_process_group()
 sys.exit(0 if t.item() == 1.0 else 1)
