@@ -308,7 +308,7 @@ def run_b200(args):
                        "solver": desc, "l2": "working set per Newton step (Jacobian 565 MB + Krylov basis) exceeds the 126 MB L2; no flush needed",
                        "parallelism": "z-slab x%d" % world},
             "nits": res.nits_vec, "lits": res.lits_vec, "dt_days": [d / 86400.0 for d in res.dt_vec],
-            "failed_solves": res.failed_solves, "host_wall_ms_per_step": wall * 1e3 / args.steps,
+            "failed_solves": res.failed_solves, "failed": res.failed, "host_wall_ms_per_step": wall * 1e3 / args.steps,
             "phase_ms": {"assemble": sum(s.t_assemble_ms for s in res.stats), "pc_setup": sum(s.t_pcsetup_ms for s in res.stats),
                          "ksp": sum(s.t_ksp_ms for s in res.stats)},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof["spmv"], "roofline_assembly": roof["assemble_FJ"],

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU consistency check (run under torchrun, one rank per GPU): a slab-partitioned assembly, SpMV
 and Newton solve must reproduce the single-domain CPU restatement.
-   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/mgpu_check.py"""
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist

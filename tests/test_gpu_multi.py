@@ -1,5 +1,5 @@
 """Slab-partitioned multi-GPU path: needs >= 2 CUDA devices (skipped on the single-GPU test box).
-Runs tools/mgpu_check.py under torchrun: assembly, SpMV and a Newton solve over 2 slabs must reproduce
+Runs tests/mgpu_check.py under torchrun: assembly, SpMV and a Newton solve over 2 slabs must reproduce
 the single-domain CPU restatement (F, J, J x to 1e-12; converged fields to 1e-8)."""
 import os
 import subprocess
@@ -16,7 +16,7 @@ def test_two_slabs_reproduce_single_domain():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29531", os.path.join(ROOT, "tools", "mgpu_check.py")]
+           "--master-port", "29531", os.path.join(ROOT, "tests", "mgpu_check.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("| OK") == 4      # two checks (kernels + Newton, model.solve()) on two ranks

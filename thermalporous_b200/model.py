@@ -35,6 +35,7 @@ class LoopResult:
         self.nits_vec, self.lits_vec, self.dt_vec, self.timings = [], [], [], []
         self.failed_solves = 0
         self.failed_time = 0.0
+        self.failed = []          # (dt, SNES reason, nits, lits) of every failed attempt
         self.chops = 0
         self.t = 0.0
         self.stats = []
@@ -72,6 +73,7 @@ def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_
         if st.reason < 0:
             res.failed_solves += 1
             res.failed_time += el
+            res.failed.append((dt_now, st.reason, st.nits, st.lits))
             raise ConvergenceError(st.reason)
         return st, el
 
