@@ -200,8 +200,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     prm = make_params()
-    refine = world
-    geo = make_geo(prm, NZ, world, args.scale)      # global grid 60 x 220 x 85*world
+    refine = max(world, args.mult)
+    geo = make_geo(prm, NZ, refine, args.scale)      # global grid 60 x 220 x 85*world
     from thermalporous_b200.partition import Slab
     slab = Slab(geo, world, rank)
     case = CS.WellCase(prm, geo, well_case="default")
@@ -335,6 +335,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scale", default="stack", choices=["stack", "refine"], help="how the grid grows with --gpus (weak scaling)")
+    ap.add_argument("--mult", type=int, default=0, help="grid multiplier when it should differ from --gpus (experiments: "
+                    "the N-rank problem on fewer ranks)")
     ap.add_argument("--opt", action="append", default=[], help="solver option override key=value (experiments)")
     args = ap.parse_args()
     if args.impl == "reference":

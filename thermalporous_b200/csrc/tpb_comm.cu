@@ -27,6 +27,8 @@ struct NcclApi {
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -47,6 +49,8 @@ NcclApi& api() {
     L(AllReduce, "ncclAllReduce");
     L(Send, "ncclSend");
     L(Recv, "ncclRecv");
+    L(Broadcast, "ncclBroadcast");
+    L(AllGather, "ncclAllGather");
     L(GroupStart, "ncclGroupStart");
     L(GroupEnd, "ncclGroupEnd");
     L(GetErrorString, "ncclGetErrorString");
@@ -80,6 +84,8 @@ struct CommState {
     double* send_first = nullptr;  // packed boundary planes (nf_max * np)
     double* send_last = nullptr;
     size_t cap = 0;
+    std::vector<int> planes;       // owned planes of every rank along the slab axis (filled on first use)
+    double* scratch = nullptr;     // nranks doubles
 };
 
 void tpb_comm_free(tpb_handle_s* h) {
@@ -87,6 +93,7 @@ void tpb_comm_free(tpb_handle_s* h) {
     if (h->comm->comm) api().CommDestroy(h->comm->comm);
     tpb_dfree(h->comm->send_first);
     tpb_dfree(h->comm->send_last);
+    tpb_dfree(h->comm->scratch);
     delete h->comm;
     h->comm = nullptr;
 }
@@ -130,6 +137,46 @@ void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count) {
 void tpb_allreduce_max(tpb_handle_s* h, double* dev_buf, int count) {
     if (!h->comm || h->comm->nranks == 1) return;
     TPB_NCCL(api().AllReduce(dev_buf, dev_buf, (size_t)count, ncclFloat64, ncclMax, h->comm->comm, h->stream));
+}
+
+// owned planes (along the slab axis) of every rank; one synchronising all-reduce on first use
+const std::vector<int>& tpb_comm_planes(tpb_handle_s* h) {
+    TPB_REQUIRE(h->comm != nullptr, TPB_ERR_STATE, "no communicator");
+    CommState* c = h->comm;
+    if ((int)c->planes.size() == c->nranks) return c->planes;
+    std::vector<double> v(c->nranks, 0.0);
+    v[c->rank] = (double)h->g.nl;
+    if (c->nranks > 1) {
+        if (!c->scratch) c->scratch = tpb_dalloc<double>(c->nranks);
+        TPB_CUDA(cudaMemcpyAsync(c->scratch, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        tpb_allreduce_sum(h, c->scratch, c->nranks);
+        TPB_CUDA(cudaMemcpyAsync(v.data(), c->scratch, v.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        TPB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    c->planes.resize(c->nranks);
+    for (int r = 0; r < c->nranks; r++) c->planes[r] = (int)(v[r] + 0.5);
+    return c->planes;
+}
+
+// in-place all-gather of pieces of different lengths: rank r's piece lives at buf + off[r] (cnt[r] doubles) on
+// every rank, `nrep` such buffers `stride` doubles apart, all in one NCCL group
+void tpb_allgatherv(tpb_handle_s* h, double* buf, const long long* off, const long long* cnt, int nrep, long long stride) {
+    if (!h->comm || h->comm->nranks == 1) return;
+    CommState* c = h->comm;
+    NcclApi& a = api();
+    bool equal = true;
+    for (int r = 1; r < c->nranks; r++) equal = equal && cnt[r] == cnt[0] && off[r] == off[0] + (long long)r * cnt[0];
+    TPB_NCCL(a.GroupStart());
+    for (int q = 0; q < nrep; q++) {
+        double* b = buf + (long long)q * stride;
+        if (equal) {
+            TPB_NCCL(a.AllGather(b + off[c->rank], b + off[0], (size_t)cnt[0], ncclFloat64, c->comm, h->stream));
+        } else {
+            for (int r = 0; r < c->nranks; r++)
+                TPB_NCCL(a.Broadcast(b + off[r], b + off[r], (size_t)cnt[r], ncclFloat64, r, c->comm, h->stream));
+        }
+    }
+    TPB_NCCL(a.GroupEnd());
 }
 
 int tpb_comm_rank(tpb_handle_s* h) { return h->comm ? h->comm->rank : 0; }

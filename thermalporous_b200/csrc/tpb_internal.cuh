@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -307,6 +308,13 @@ void tpb_launch_assemble(tpb_handle_s* h, const double* u, const double* u_old, 
 void tpb_launch_spmv(tpb_handle_s* h, const double* J, const double* x, double* y);
 void tpb_halo_vector(tpb_handle_s* h, const double* x, int nfields, double* lo, double* hi);
 void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count);
+int tpb_comm_rank(tpb_handle_s* h);
+int tpb_comm_size(tpb_handle_s* h);
+const std::vector<int>& tpb_comm_planes(tpb_handle_s* h);
+void tpb_allgatherv(tpb_handle_s* h, double* buf, const long long* off, const long long* cnt, int nrep, long long stride);
+// A communication step (NCCL) inside code that may be under CUDA-graph capture (the PC application): run now when
+// nothing is being captured; otherwise the capture is cut into two graphs around it (tpb_pc.cu).
+void tpb_comm_op(tpb_handle_s* h, const std::function<void()>& op);
 
 // blas-1 (tpb_blas.cu)
 void tpb_axpy(tpb_handle_s* h, size_t n, double a, const double* x, double* y);          // y += a x

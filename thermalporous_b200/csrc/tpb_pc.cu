@@ -33,13 +33,27 @@ struct MgLevel {
     int cx = 1, cy = 1, cz = 1;
     double* a = nullptr;  // ns * n
     bool own_a = false;
-    double* x = nullptr;
-    double* b = nullptr;
+    double* x = nullptr;  // the vectors the cycle works on: the level's own storage, or (gather level of a
+    double* b = nullptr;  // multi-rank hierarchy) this rank's section of the gathered level
+    double* x_own = nullptr;
+    double* b_own = nullptr;
 };
 
+// Multi-rank slabs (K7 over NCCL): every rank coarsens its own slab with globally agreed coarsening factors
+// until the levels of all ranks together hold <= GATHER_CELLS cells.  That level is all-gathered (operator at
+// set-up, right-hand side once per V-cycle) - slabs are cut along the slowest axis, so the concatenation of the
+// ranks' arrays IS the global level, and the couplings across slab faces that the Galerkin sums carried down in
+// the boundary slots become interior couplings there.  Every rank then runs the remaining levels (`glob`)
+// redundantly on identical data (bitwise identical results, no second exchange) and prolongs from its section.
+// The levels above the gather level smooth with the couplings across slab faces dropped (block-Jacobi between
+// slabs, Gauss-Seidel inside - what hypre's hybrid smoother does between processes).
 struct MgHier {
     int nlev = 0;
     MgLevel lev[MAXLEV];
+    MgHier* glob = nullptr;
+    double* ga = nullptr;          // gathered operator of the gather level (ns * gn)
+    long long ga_cap = 0;
+    std::vector<long long> gcnt, goff;   // cells of every rank on the gather level and their offsets
 };
 
 }  // namespace
@@ -56,11 +70,21 @@ struct PcState {
     double *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
     double* strength = nullptr;  // 3 doubles (device)
     bool ready = false;
-    // the whole PC apply (~100 small dependent kernels) replayed as one CUDA graph on fixed in/out buffers
-    cudaGraphExec_t gexec = nullptr, gexec2 = nullptr;
+    // the whole PC apply (~100 small dependent kernels) replayed from CUDA graphs on fixed in/out buffers: one
+    // graph on a single slab; on slabs with neighbours a short program of graphs with the NCCL steps (all-gather
+    // of each V-cycle's gather level, halo exchange of the residual SpMV) between them
+    struct Item {
+        cudaGraphExec_t g = nullptr;
+        int64_t nodes = 0;
+        std::function<void()> op;
+    };
+    std::vector<Item> prog;
+    std::vector<cudaGraphExec_t> spare;   // executables of the previous set-up, re-used through cudaGraphExecUpdate
+    size_t spare_next = 0;
+    bool capturing = false;
+    int64_t cap_l0 = 0;
     double *gx = nullptr, *gy = nullptr;
-    int64_t graph_nodes = 0, graph_nodes2 = 0;
-    bool graph_ok = false, split = false;
+    bool graph_ok = false;
 };
 
 namespace {
@@ -209,17 +233,26 @@ __global__ void __launch_bounds__(128) cptr_setup_kernel(const double* __restric
 struct CdCell {
     double p, T, ro, rw, lo, lw, kT;
 };
+// inputs of the ConvDiff operator with the slab's ghost planes (state ghosts are the ones the assembly of the
+// same Newton state exchanged)
+struct CdIn {
+    GField u[TPB_MAXF];
+    GField phi, K[3], kT;
+};
+__device__ __forceinline__ double cd_gl(const GField& f, long long c, long long n, int np) {
+    return c < 0 ? f.lo[c + np] : (c >= n ? f.hi[c - n] : f.v[c]);
+}
 template <int NF>
-__device__ __forceinline__ CdCell cd_props(const DevParams& P, const double* __restrict__ u, long long n, long long c,
-                                           double phi, double kTs) {
+__device__ __forceinline__ CdCell cd_props(const DevParams& P, const CdIn& in, long long n, int np, long long c) {
     CdCell q;
-    q.p = u[c];
-    q.T = u[n + c];
+    q.p = cd_gl(in.u[0], c, n, np);
+    q.T = cd_gl(in.u[1], c, n, np);
     double a, b, imo, imo_T;
     oil_rho_d(P, q.p, q.T, q.ro, a, b);
     oil_imu_d(P, q.T, imo, imo_T);
     if (NF == 3) {
-        double S = u[2 * n + c], imw, imw_T;
+        double S = cd_gl(in.u[2], c, n, np), imw, imw_T;
+        double phi = cd_gl(in.phi, c, n, np);
         water_rho_d(q.p, q.T, q.rw, a, b);
         water_imu_d(q.T, imw, imw_T);
         q.lo = S * q.ro * imo;
@@ -229,7 +262,7 @@ __device__ __forceinline__ CdCell cd_props(const DevParams& P, const double* __r
         q.rw = 0.0;
         q.lw = 0.0;
         q.lo = q.ro * imo;
-        q.kT = kTs;
+        q.kT = cd_gl(in.kT, c, n, np);
     }
     return q;
 }
@@ -239,37 +272,46 @@ __device__ __forceinline__ double harm_d(double a, double b) {
 }
 
 template <int NF, int DIM>
-__global__ void __launch_bounds__(128) convdiff_kernel(const double* __restrict__ u, const double* __restrict__ phi_f,
-                                                       const double* __restrict__ Kx, const double* __restrict__ Ky,
-                                                       const double* __restrict__ Kz, const double* __restrict__ kT_f,
-                                                       double idt, Geom g, DevParams P, double* __restrict__ A) {
+__global__ void __launch_bounds__(128) convdiff_kernel(CdIn in, double idt, Geom g, DevParams P, double* __restrict__ A) {
     const long long n = g.n;
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
-    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int nx = g.nx, ny = g.ny, nz = g.nz, np = g.np;
     int i, j, k;
     tpb_ijk(c, nx, ny, i, j, k);
-    double phi = phi_f[c];
-    CdCell me = cd_props<NF>(P, u, n, c, phi, NF == 2 ? kT_f[c] : 0.0);
+    double phi = in.phi.v[c];
+    CdCell me = cd_props<NF>(P, in, n, np, c);
     double diag;
     if (NF == 2)
         diag = g.vol * idt * (phi * P.c_v_o * me.ro + (1.0 - phi) * P.rho_r * P.c_r);
     else {
-        double S = u[2 * n + c];
+        double S = in.u[2].v[c];
         diag = g.vol * idt * (phi * P.c_v_o * S * me.ro + phi * P.c_v_w * (1.0 - S) * me.rw + (1.0 - phi) * P.rho_r * P.c_r);
     }
 #pragma unroll
     for (int s = 1; s < 2 * DIM + 1; s++) {
-        long long nb = nbr_cell(nx, ny, nz, i, j, k, c, s);
+        const int axis = (s - 1) >> 1;
+        const bool hi = ((s - 1) & 1) != 0;
+        // neighbour through slot s; across a slab face it lives in a ghost plane (index < 0 or >= n)
+        bool ex;
+        long long nb;
+        if (axis == 0) {
+            ex = hi ? (i < nx - 1) : (i > 0);
+            nb = c + (hi ? 1 : -1);
+        } else if (axis == 1) {
+            ex = hi ? (j < ny - 1 || (DIM == 2 && g.has_hi)) : (j > 0 || (DIM == 2 && g.has_lo));
+            nb = c + (hi ? nx : -nx);
+        } else {
+            ex = hi ? (k < nz - 1 || g.has_hi) : (k > 0 || g.has_lo);
+            nb = c + (hi ? (long long)np : -(long long)np);
+        }
         double off = 0.0;
-        if (nb >= 0) {
-            const int axis = (s - 1) >> 1;
-            const bool hi = ((s - 1) & 1) != 0;
-            const double* Kax = axis == 0 ? Kx : (axis == 1 ? Ky : Kz);
-            CdCell ot = cd_props<NF>(P, u, n, nb, phi_f[nb], NF == 2 ? kT_f[nb] : 0.0);
+        if (ex) {
+            const GField& Kax = in.K[axis];
+            CdCell ot = cd_props<NF>(P, in, n, np, nb);
             const CdCell& pl = hi ? me : ot;
             const CdCell& mi = hi ? ot : me;
-            double Kf = harm_d(Kax[c], Kax[nb]);
+            double Kf = harm_d(Kax.v[c], cd_gl(Kax, nb, n, np));
             double grav = axis == 2 ? P.g : 0.0;
             double ih = 1.0 / g.h[axis], area = g.area[axis];
             double dp = ih * (pl.p - mi.p);
@@ -648,6 +690,18 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
     cyc_up<NS>(A, A.nlev - 1, 0, tid, nth, bar);
 }
 
+// multi-rank hierarchies: the single-CTA zone above the gather level is cut in two around the all-gather
+template <int NS>
+__global__ void __launch_bounds__(TAIL_THREADS) tail_down_kernel(TailArgs A) {
+    BlockBarrier bar;
+    cyc_down<NS>(A, 0, A.nlev - 1, (long long)threadIdx.x, (long long)blockDim.x, bar);
+}
+template <int NS>
+__global__ void __launch_bounds__(TAIL_THREADS) tail_up_kernel(TailArgs A) {
+    BlockBarrier bar;
+    cyc_up<NS>(A, A.nlev - 1, 0, (long long)threadIdx.x, (long long)blockDim.x, bar);
+}
+
 // ---- K6 / coupling kernels ----------------------------------------------------------------------
 // CPR restriction: rp = x_p - sum_f w_f x_f
 template <int NF>
@@ -831,24 +885,49 @@ inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads 
 
 inline LevGeom lg(const MgLevel& L) { return LevGeom{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.n}; }
 
-void mg_free(MgHier& m) {
+void mg_free_levels(MgHier& m) {
     for (int l = 0; l < m.nlev; l++) {
         if (m.lev[l].own_a) tpb_dfree(m.lev[l].a);
-        tpb_dfree(m.lev[l].x);
-        tpb_dfree(m.lev[l].b);
+        tpb_dfree(m.lev[l].x_own);
+        tpb_dfree(m.lev[l].b_own);
         m.lev[l] = MgLevel();
     }
     m.nlev = 0;
 }
 
+void mg_free(MgHier& m) {
+    mg_free_levels(m);
+    if (m.glob) {
+        mg_free_levels(*m.glob);
+        delete m.glob;
+        m.glob = nullptr;
+    }
+    tpb_dfree(m.ga);
+    m.ga = nullptr;
+    m.ga_cap = 0;
+}
+
+// cells of all ranks on the gather level of a multi-rank hierarchy (TPB_MG_GATHER overrides); levels of at most
+// TAIL_CELLS cells run inside one CTA, so with the default the whole global part of a V-cycle is one kernel
+long long gather_cells() {
+    static const long long v = getenv("TPB_MG_GATHER") ? atoll(getenv("TPB_MG_GATHER")) : 4096;   // = TAIL_CELLS
+    return v;
+}
+
+// Builds levels 1.. of `m` from the level-0 operator a0 on an (nx, ny, nz) box.  dist: the box is this rank's
+// slab; coarsening factors are agreed between the ranks (all-reduced coupling sums, the largest slab decides
+// whether the slab axis can still be halved) and coarsening stops at the gather level.  planes: owned planes of
+// every rank along the slab axis, updated to the last level built.
 template <int NS>
-void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
+void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int nz0, bool dist, std::vector<int>& planes) {
     PcState* pc = h->pc;
     const tpb_solver_opts& o = h->opts;
     // geometry of level 0 never changes between set-ups, and the coarsening schedule is recomputed from
     // the operator each time (as hypre's set-up is, preconditioners.py:878), so levels are re-allocated
     // only when their shape changes
-    MgHier old = m;
+    MgHier old;
+    old.nlev = m.nlev;
+    for (int l = 0; l < m.nlev; l++) old.lev[l] = m.lev[l];
     MgHier nw;
     auto take = [&](int l, int nx, int ny, int nz) -> MgLevel {
         MgLevel L;
@@ -858,42 +937,59 @@ void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
             old.lev[l] = MgLevel();
         } else {
             L.cap = n + n / 8 + 64;   // head-room: the coarsening schedule shifts a little between set-ups
-            L.x = tpb_dalloc<double>(L.cap);
-            L.b = tpb_dalloc<double>(L.cap);
+            L.x_own = tpb_dalloc<double>(L.cap);
+            L.b_own = tpb_dalloc<double>(L.cap);
             if (l > 0) {
                 L.a = tpb_dalloc<double>((size_t)NS * L.cap);
                 L.own_a = true;
             }
         }
+        L.x = L.x_own;
+        L.b = L.b_own;
         L.nx = nx;
         L.ny = ny;
         L.nz = nz;
         L.n = n;
         return L;
     };
+    const int sax = h->g.dim - 1;   // slab axis
     int l = 0;
-    nw.lev[0] = take(0, h->g.nx, h->g.ny, h->g.nz);
+    nw.lev[0] = take(0, nx0, ny0, nz0);
+    if (nw.lev[0].own_a) tpb_dfree(nw.lev[0].a);
     nw.lev[0].a = a0;
     nw.lev[0].own_a = false;
     for (;;) {
         MgLevel& L = nw.lev[l];
         L.cx = L.cy = L.cz = 1;
-        if (L.n <= o.mg_min_cells || L.n <= 1 || l == MAXLEV - 1) break;
+        int dims[3] = {L.nx, L.ny, L.nz};
+        long long nglob = L.n;
+        if (dist) {
+            long long tot = 0;
+            int mx = 0;
+            for (int p : planes) {
+                tot += p;
+                mx = std::max(mx, p);
+            }
+            nglob = L.n / dims[sax] * tot;
+            dims[sax] = mx;
+        }
+        const long long stop_at = dist ? std::max<long long>(gather_cells(), o.mg_min_cells) : o.mg_min_cells;
+        if (nglob <= stop_at || nglob <= 1 || l == MAXLEV - 1) break;
         TPB_CUDA(cudaMemsetAsync(pc->strength, 0, 3 * sizeof(double), h->stream));
         unsigned blocks = std::min<unsigned>(nblk(L.n, 256), 1184u);
         strength_kernel<NS><<<blocks, 256, 0, h->stream>>>(L.a, L.n, pc->strength);
         h->launches++;
+        if (dist) tpb_allreduce_sum(h, pc->strength, 3);
         double m_ax[3];
         TPB_CUDA(cudaMemcpyAsync(m_ax, pc->strength, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         TPB_CUDA(cudaStreamSynchronize(h->stream));
-        int dims[3] = {L.nx, L.ny, L.nz};
         double mmax = 0.0;
         for (int ax = 0; ax < 3; ax++)
             if (dims[ax] > 1 && m_ax[ax] > mmax) mmax = m_ax[ax];
         int cf[3] = {1, 1, 1};
         bool any = false;
         for (int ax = 0; ax < 3; ax++)
-            if (dims[ax] > 1 && (m_ax[ax] >= o.mg_semi_theta * mmax || L.n <= o.mg_full_below)) {
+            if (dims[ax] > 1 && (m_ax[ax] >= o.mg_semi_theta * mmax || nglob <= o.mg_full_below)) {
                 cf[ax] = 2;
                 any = true;
             }
@@ -908,15 +1004,61 @@ void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
         L.cy = cf[1];
         L.cz = cf[2];
         nw.lev[l + 1] = take(l + 1, (L.nx + cf[0] - 1) / cf[0], (L.ny + cf[1] - 1) / cf[1], (L.nz + cf[2] - 1) / cf[2]);
+        if (dist)
+            for (int& p : planes) p = (p + cf[sax] - 1) / cf[sax];
         MgLevel& Cc = nw.lev[l + 1];
         coarsen_op_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, lg(L), lg(Cc), Cc.a);
         h->launches++;
         l++;
     }
     nw.nlev = l + 1;
-    mg_free(old);
-    m = nw;
+    mg_free_levels(old);
+    m.nlev = nw.nlev;
+    for (int q = 0; q < MAXLEV; q++) m.lev[q] = q < nw.nlev ? nw.lev[q] : MgLevel();
     TPB_CUDA(cudaGetLastError());
+}
+
+template <int NS>
+void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
+    const int nranks = tpb_comm_size(h);
+    const bool dist = nranks > 1;
+    std::vector<int> planes;
+    if (dist) planes = tpb_comm_planes(h);
+    mg_coarsen_t<NS>(h, m, a0, h->g.nx, h->g.ny, h->g.nz, dist, planes);
+    if (!dist) return;
+    // ---- gather level: concatenate the ranks' last levels along the slab axis ----------------------
+    const int rank = tpb_comm_rank(h);
+    MgLevel& L = m.lev[m.nlev - 1];
+    const int sax = h->g.dim - 1;
+    const int ldims[3] = {L.nx, L.ny, L.nz};
+    const long long npl = L.n / ldims[sax];   // cells per plane of the slab axis on this level
+    m.gcnt.assign(nranks, 0);
+    m.goff.assign(nranks, 0);
+    long long gn = 0, gplanes = 0;
+    for (int r = 0; r < nranks; r++) {
+        m.goff[r] = gn;
+        m.gcnt[r] = npl * planes[r];
+        gn += m.gcnt[r];
+        gplanes += planes[r];
+    }
+    TPB_REQUIRE(m.gcnt[rank] == L.n, TPB_ERR_STATE, "multigrid gather level: slab sizes disagree between ranks");
+    if (m.ga_cap < gn) {
+        tpb_dfree(m.ga);
+        m.ga_cap = gn + gn / 8 + 64;
+        m.ga = tpb_dalloc<double>((size_t)NS * m.ga_cap);
+    }
+    for (int s = 0; s < NS; s++)
+        TPB_CUDA(cudaMemcpyAsync(m.ga + (long long)s * gn + m.goff[rank], L.a + (long long)s * L.n, L.n * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    tpb_allgatherv(h, m.ga, m.goff.data(), m.gcnt.data(), NS, gn);
+    if (!m.glob) m.glob = new MgHier();
+    int gd[3] = {L.nx, L.ny, L.nz};
+    gd[sax] = (int)gplanes;
+    std::vector<int> none;
+    mg_coarsen_t<NS>(h, *m.glob, m.ga, gd[0], gd[1], gd[2], false, none);
+    // the gather level works directly on this rank's section of the gathered vectors
+    L.x = m.glob->lev[0].x + m.goff[rank];
+    L.b = m.glob->lev[0].b + m.goff[rank];
 }
 
 void mg_setup(tpb_handle_s* h, MgHier& m, double* a0) {
@@ -947,14 +1089,30 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     const tpb_solver_opts& o = h->opts;
     const int pre = o.mg_pre > 0 ? o.mg_pre : 1;
     const int coarse = o.mg_coarse_sweeps > 0 ? o.mg_coarse_sweeps : 1;
-    // level zones: [0, lcoop) one kernel per colour pass, [lcoop, nlev) inside one CTA (the tail)
-    int ltail = m.nlev - 1;
+    const bool dist = m.glob != nullptr;   // the last level is the gather level: smoothed as level 0 of m.glob
+    const int last = m.nlev - 1;
+    // level zones: [0, lcoop) one kernel per colour pass, [ltail, last] inside one CTA (levels <= TAIL_CELLS)
+    int ltail = m.nlev;
     while (ltail > 0 && m.lev[ltail - 1].n <= TAIL_CELLS) ltail--;
-    if (m.lev[ltail].n > TAIL_CELLS) ltail = m.nlev;  // no tail at all (coarsest too large)
-    const int lcoop = ltail;
-    for (int l = 0; l < lcoop && l < m.nlev; l++) {
+    const int lcoop = std::min(ltail, dist ? last : m.nlev);
+    auto tail_args = [&](int l0) {
+        TailArgs A;
+        A.nlev = m.nlev - l0;
+        for (int l = l0; l < m.nlev; l++) {
+            A.lev[l - l0].g = lg(m.lev[l]);
+            A.lev[l - l0].a = m.lev[l].a;
+            A.lev[l - l0].x = m.lev[l].x;
+            A.lev[l - l0].b = m.lev[l].b;
+        }
+        A.pre = pre;
+        A.post = o.mg_post;
+        A.coarse_sweeps = coarse;
+        A.omega = o.mg_overcorrection;
+        return A;
+    };
+    for (int l = 0; l < lcoop; l++) {
         MgLevel& L = m.lev[l];
-        if (l == m.nlev - 1) {
+        if (!dist && l == last) {
             for (int s = 0; s < coarse; s++) mg_rbgs<NS>(h, L, s == 0);
             break;
         }
@@ -963,23 +1121,27 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         restrict_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
         h->launches++;
     }
-    if (lcoop < m.nlev) {
-        TailArgs A;
-        A.nlev = m.nlev - lcoop;
-        for (int l = lcoop; l < m.nlev; l++) {
-            A.lev[l - lcoop].g = lg(m.lev[l]);
-            A.lev[l - lcoop].a = m.lev[l].a;
-            A.lev[l - lcoop].x = m.lev[l].x;
-            A.lev[l - lcoop].b = m.lev[l].b;
+    if (!dist) {
+        if (ltail < m.nlev) {
+            tail_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(tail_args(ltail));
+            h->launches++;
         }
-        A.pre = pre;
-        A.post = o.mg_post;
-        A.coarse_sweeps = coarse;
-        A.omega = o.mg_overcorrection;
-        tail_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(A);
-        h->launches++;
+    } else {
+        if (ltail < last) {
+            tail_down_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(tail_args(ltail));
+            h->launches++;
+        }
+        MgHier* mp = &m;
+        tpb_comm_op(h, [h, mp]() {
+            tpb_allgatherv(h, mp->glob->lev[0].b, mp->goff.data(), mp->gcnt.data(), 1, 0);
+        });
+        mg_vcycle_t<NS>(h, *m.glob);
+        if (ltail < last) {
+            tail_up_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(tail_args(ltail));
+            h->launches++;
+        }
     }
-    for (int l = std::min(lcoop, m.nlev - 1) - 1; l >= 0; l--) {
+    for (int l = std::min(lcoop, last) - 1; l >= 0; l--) {
         MgLevel& L = m.lev[l];
         MgLevel& Cc = m.lev[l + 1];
         if (o.mg_post > 0) {
@@ -998,14 +1160,22 @@ template <int NS>
 void mg_apply_t(tpb_handle_s* h, MgHier& m, const double* b, double* y) {
     MgLevel& L = m.lev[0];
     const int cycles = h->opts.mg_cycles > 0 ? h->opts.mg_cycles : 1;
-    double* keep_b = L.b;
-    double* keep_x = L.x;
-    // run level 0 directly on the caller's vectors (no copies)
-    L.b = const_cast<double*>(b);
-    L.x = y;
-    mg_vcycle_t<NS>(h, m);
-    L.b = keep_b;
-    L.x = keep_x;
+    if (m.glob && m.nlev == 1) {
+        // level 0 is itself the gather level (small grids on several ranks): its vectors are sections of the
+        // gathered level, so copy in and out
+        tpb_copy(h, (size_t)L.n, b, L.b);
+        mg_vcycle_t<NS>(h, m);
+        tpb_copy(h, (size_t)L.n, L.x, y);
+    } else {
+        double* keep_b = L.b;
+        double* keep_x = L.x;
+        // run level 0 directly on the caller's vectors (no copies)
+        L.b = const_cast<double*>(b);
+        L.x = y;
+        mg_vcycle_t<NS>(h, m);
+        L.b = keep_b;
+        L.x = keep_x;
+    }
     for (int cyc = 1; cyc < cycles; cyc++) {
         residual_kernel<NS><<<nblk(L.n, 256), 256, 0, h->stream>>>(L.a, b, y, lg(L), L.b);
         h->launches++;
@@ -1045,9 +1215,19 @@ void stage1_setup_t(tpb_handle_s* h, const double* J, const double* u, double dt
                                                                    pc->App, pc->AT);
     h->launches++;
     if (!a11) {
-        convdiff_kernel<NF, DIM><<<nblk(n, 128), 128, 0, h->stream>>>(u, h->fld[TPB_PHI], h->fld[TPB_KX], h->fld[TPB_KY],
-                                                                     h->fld[DIM == 3 ? TPB_KZ : TPB_KY], h->fld[TPB_KT],
-                                                                     1.0 / dt, h->g, h->dp, pc->AT);
+        CdIn in;
+        const int np = h->g.np;
+        for (int f = 0; f < TPB_MAXF; f++) {
+            const int ff = f < NF ? f : 0;
+            in.u[f] = GField{u + (size_t)ff * n, h->u_lo + (size_t)ff * np, h->u_hi + (size_t)ff * np};
+        }
+        auto gf = [&](int id) { return GField{h->fld[id], h->fld_lo[id], h->fld_hi[id]}; };
+        in.phi = gf(TPB_PHI);
+        in.K[0] = gf(TPB_KX);
+        in.K[1] = gf(TPB_KY);
+        in.K[2] = gf(DIM == 3 ? TPB_KZ : TPB_KY);
+        in.kT = gf(TPB_KT);
+        convdiff_kernel<NF, DIM><<<nblk(n, 128), 128, 0, h->stream>>>(in, 1.0 / dt, h->g, h->dp, pc->AT);
         h->launches++;
         if (h->nsrc_cells > 0) {
             convdiff_sources_kernel<NF><<<nblk(h->nsrc_cells, 128), 128, 0, h->stream>>>(
@@ -1133,24 +1313,11 @@ void pc_setup_t(tpb_handle_s* h, const double* J, const double* u, double dt) {
     stage2_setup_t<NF, DIM>(h, J);
 }
 
-// part 0: the whole application; part 1: stage 1 only; part 2: what follows the residual SpMV (t0 holds J y).
-// The split exists for slabs with neighbours: the SpMV needs an NCCL halo exchange, which stays outside the
-// two CUDA graphs that replay parts 1 and 2.
 template <int NF, int DIM>
-void pc_apply_t(tpb_handle_s* h, const double* x, double* y, int part = 0) {
+void pc_apply_t(tpb_handle_s* h, const double* x, double* y) {
     PcState* pc = h->pc;
     const tpb_solver_opts& o = h->opts;
     const size_t nd = (size_t)NF * h->g.n;
-    if (part == 1) {
-        stage1_apply_t<NF, DIM>(h, x, y);
-        return;
-    }
-    if (part == 2) {
-        tpb_axpby(h, nd, 1.0, x, -1.0, pc->t0);  // t0 = x - J y
-        stage2_apply_t<NF, DIM>(h, pc->t0, pc->t1);
-        tpb_axpy(h, nd, 1.0, pc->t1, y);
-        return;
-    }
     if (o.stage1 == TPB_S1_NONE && o.stage2 == TPB_S2_NONE) {
         tpb_copy(h, nd, x, y);
         return;
@@ -1161,7 +1328,7 @@ void pc_apply_t(tpb_handle_s* h, const double* x, double* y, int part = 0) {
     }
     stage1_apply_t<NF, DIM>(h, x, y);
     if (o.stage2 == TPB_S2_NONE || o.stage1 == TPB_S1_FIELDSPLIT) return;
-    tpb_launch_spmv(h, pc->J, y, pc->t0);
+    tpb_launch_spmv(h, pc->J, y, pc->t0);   // on slabs with neighbours: NCCL halo exchange of y first
     tpb_axpby(h, nd, 1.0, x, -1.0, pc->t0);  // t0 = x - J y
     stage2_apply_t<NF, DIM>(h, pc->t0, pc->t1);
     tpb_axpy(h, nd, 1.0, pc->t1, y);
@@ -1201,16 +1368,80 @@ void tpb_pc_free(tpb_handle_s* h) {
     tpb_dfree(pc->t2);
     tpb_dfree(pc->t3);
     tpb_dfree(pc->strength);
-    if (pc->gexec) cudaGraphExecDestroy(pc->gexec);
-    if (pc->gexec2) cudaGraphExecDestroy(pc->gexec2);
+    for (auto& it : pc->prog)
+        if (it.g) cudaGraphExecDestroy(it.g);
+    for (auto g : pc->spare)
+        if (g) cudaGraphExecDestroy(g);
     tpb_dfree(pc->gx);
     tpb_dfree(pc->gy);
     delete pc;
     h->pc = nullptr;
 }
 
+namespace {
+
+// TPB_GRAPH_NCCL=1: leave the NCCL calls inside the capture (one graph per application) instead of cutting the
+// capture around them
+bool capture_nccl() {
+    static const bool v = getenv("TPB_GRAPH_NCCL") && atoi(getenv("TPB_GRAPH_NCCL")) != 0;
+    return v;
+}
+
+void seg_begin(tpb_handle_s* h) {
+    TPB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    h->pc->capturing = true;
+    h->pc->cap_l0 = h->launches;
+}
+
+// close the running capture and append it to the program (dropped when it recorded nothing)
+void seg_end(tpb_handle_s* h) {
+    PcState* pc = h->pc;
+    cudaGraph_t graph = nullptr;
+    pc->capturing = false;
+    TPB_CUDA(cudaStreamEndCapture(h->stream, &graph));
+    const int64_t nodes = h->launches - pc->cap_l0;
+    h->launches = pc->cap_l0;
+    size_t nn = 0;
+    TPB_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
+    if (nn == 0) {
+        cudaGraphDestroy(graph);
+        return;
+    }
+    cudaGraphExec_t gexec = nullptr;
+    if (pc->spare_next < pc->spare.size()) {
+        gexec = pc->spare[pc->spare_next];
+        pc->spare[pc->spare_next++] = nullptr;
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(gexec, graph, &info) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphExecDestroy(gexec);
+            gexec = nullptr;
+        }
+    }
+    if (!gexec) TPB_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+    cudaGraphDestroy(graph);
+    PcState::Item it;
+    it.g = gexec;
+    it.nodes = nodes;
+    pc->prog.push_back(it);
+}
+
+}  // namespace
+
+void tpb_comm_op(tpb_handle_s* h, const std::function<void()>& op) {
+    PcState* pc = h->pc;
+    if (!pc || !pc->capturing || capture_nccl()) {
+        op();
+        return;
+    }
+    seg_end(h);
+    PcState::Item it;
+    it.op = op;
+    pc->prog.push_back(it);
+    seg_begin(h);
+}
+
 void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double dt) {
-    TPB_REQUIRE(!(h->g.has_lo || h->g.has_hi) || h->opts.stage1 == TPB_S1_NONE || true, TPB_ERR_UNSUPPORTED, "");
     if (!h->pc) {
         h->pc = new PcState();
         const size_t nd = (size_t)h->nf * h->g.n;
@@ -1224,59 +1455,44 @@ void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double
     DISPATCH(pc_setup_t, h, J, u, dt);
     TPB_CUDA(cudaGetLastError());
     h->pc->ready = true;
-    // Capture one application into a CUDA graph: the Krylov loop applies the PC 20-30 times per set-up and
-    // replaying removes the host-side launch cost of its ~100 small kernels.  Slabs with neighbours need an
-    // NCCL halo exchange for the residual SpMV of the multiplicative composite, so there the application is
-    // two graphs (stage 1 | stage 2) around that SpMV.  TPB_GRAPH=0 disables it.
+    // Capture one application into CUDA graphs: the Krylov loop applies the PC 20-30 times per set-up and
+    // replaying removes the host-side launch cost of its ~100 small kernels.  TPB_GRAPH=0 disables it.
     PcState* pc = h->pc;
     pc->graph_ok = false;
-    pc->split = false;
     static const bool want = !(getenv("TPB_GRAPH") && atoi(getenv("TPB_GRAPH")) == 0);
     const tpb_solver_opts& o = h->opts;
     const bool any = o.stage1 != TPB_S1_NONE || o.stage2 != TPB_S2_NONE;
-    const bool halo = h->g.has_lo || h->g.has_hi;
-    const bool two_stage = o.stage1 != TPB_S1_NONE && o.stage2 != TPB_S2_NONE && o.stage1 != TPB_S1_FIELDSPLIT;
     if (want && any) {
         const size_t nd = (size_t)h->nf * h->g.n;
         if (!pc->gx) pc->gx = tpb_dalloc<double>(nd);
         if (!pc->gy) pc->gy = tpb_dalloc<double>(nd);
-        pc->split = halo && two_stage;
-        auto capture = [&](int part, cudaGraphExec_t& gexec, int64_t& nodes) {
-            cudaGraph_t graph = nullptr;
-            const int64_t l0 = h->launches;
-            TPB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            try {
-                DISPATCH(pc_apply_t, h, pc->gx, pc->gy, part);
-            } catch (...) {
-                cudaStreamEndCapture(h->stream, &graph);
-                if (graph) cudaGraphDestroy(graph);
-                throw;
-            }
-            TPB_CUDA(cudaStreamEndCapture(h->stream, &graph));
-            nodes = h->launches - l0;
-            h->launches = l0;
-            bool updated = false;
-            if (gexec) {
-                cudaGraphExecUpdateResultInfo info;
-                updated = cudaGraphExecUpdate(gexec, graph, &info) == cudaSuccess;
-                if (!updated) {
-                    cudaGetLastError();
-                    cudaGraphExecDestroy(gexec);
-                    gexec = nullptr;
-                }
-            }
-            if (!updated) TPB_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
-            cudaGraphDestroy(graph);
-        };
-        if (pc->split) {
-            capture(1, pc->gexec, pc->graph_nodes);
-            capture(2, pc->gexec2, pc->graph_nodes2);
-            pc->graph_ok = true;
-        } else if (!halo || !two_stage) {
-            // single slab, or an application without the residual SpMV (no NCCL inside)
-            capture(0, pc->gexec, pc->graph_nodes);
-            pc->graph_ok = true;
+        for (auto g : pc->spare)
+            if (g) cudaGraphExecDestroy(g);
+        pc->spare.clear();
+        for (auto& it : pc->prog)
+            if (it.g) pc->spare.push_back(it.g);
+        pc->spare_next = 0;
+        pc->prog.clear();
+        if (capture_nccl() && tpb_comm_size(h) > 1) {
+            // NCCL connects its channels lazily: run the application once outside any capture first
+            DISPATCH(pc_apply_t, h, pc->gx, pc->gy);
+            TPB_CUDA(cudaStreamSynchronize(h->stream));
         }
+        seg_begin(h);
+        try {
+            DISPATCH(pc_apply_t, h, pc->gx, pc->gy);
+        } catch (...) {
+            cudaGraph_t graph = nullptr;
+            pc->capturing = false;
+            cudaStreamEndCapture(h->stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        seg_end(h);
+        for (auto g : pc->spare)
+            if (g) cudaGraphExecDestroy(g);
+        pc->spare.clear();
+        pc->graph_ok = true;
     }
 }
 
@@ -1286,12 +1502,13 @@ void tpb_pc_apply_impl(tpb_handle_s* h, const double* x, double* y) {
     if (pc->graph_ok) {
         const size_t nd = (size_t)h->nf * h->g.n;
         TPB_CUDA(cudaMemcpyAsync(pc->gx, x, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-        TPB_CUDA(cudaGraphLaunch(pc->gexec, h->stream));
-        h->launches += pc->graph_nodes;
-        if (pc->split) {
-            tpb_launch_spmv(h, pc->J, pc->gy, pc->t0);   // with its NCCL halo exchange
-            TPB_CUDA(cudaGraphLaunch(pc->gexec2, h->stream));
-            h->launches += pc->graph_nodes2;
+        for (auto& it : pc->prog) {
+            if (it.g) {
+                TPB_CUDA(cudaGraphLaunch(it.g, h->stream));
+                h->launches += it.nodes;
+            } else {
+                it.op();
+            }
         }
         TPB_CUDA(cudaMemcpyAsync(y, pc->gy, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         return;
