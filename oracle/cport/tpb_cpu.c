@@ -575,6 +575,18 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
     const tpb_solver_opts* o = &h->opts;
     const int ns = h->g.ns;
     mg_free(m);
+    /* row repair (csrc/tpb_pc.cu row_repair_kernel): a diagonal far below the sum of the row's couplings is raised
+     * to that sum - rows of cells whose Newton iterate left the physical range (S_o outside [0,1]) would
+     * otherwise make Gauss-Seidel diverge */
+    {
+        const long n0 = h->g.n;
+#pragma omp parallel for schedule(static)
+        for (long c = 0; c < n0; c++) {
+            double sum = 0.0;
+            for (int s = 1; s < ns; s++) sum += fabs(a0[(long)s * n0 + c]);
+            if (a0[c] < 0.8 * sum) a0[c] = sum;
+        }
+    }
     mglevel* L = &m->lev[0];
     L->nx = h->g.nx;
     L->ny = h->g.ny;
@@ -1190,7 +1202,27 @@ static void ksp_solve(tpc_handle_s* h, const double* J, const double* b, double*
 #pragma omp parallel for schedule(static)
                 for (long q = 0; q < nd; q++) wv[q] -= hj * vj[q];
             }
-            double hn = sqrt(vdot(nd, wv, wv));
+            /* second Gram-Schmidt pass once the residual is below 1e-3 ||b|| (csrc/tpb_solver.cu REFINE_AT):
+             * unrefined CGS loses orthogonality like eps (||b||/||r||)^2 and stalls short of rtol = 1e-8 */
+            double hn = -1.0;
+            if (rnorm <= 1e-3 * bnorm) {
+                double* cc = yv; /* scratch: yv is only used after the cycle */
+                for (int jv = 0; jv <= k; jv++) cc[jv] = vdot(nd, wv, V + (long)jv * nd);
+                const double ww = vdot(nd, wv, wv);
+                double c2 = 0.0;
+                for (int jv = 0; jv <= k; jv++) {
+                    c2 += cc[jv] * cc[jv];
+                    Hk[jv] += cc[jv];
+                }
+                for (int jv = 0; jv <= k; jv++) {
+                    const double hj = cc[jv];
+                    const double* vj = V + (long)jv * nd;
+#pragma omp parallel for schedule(static)
+                    for (long q = 0; q < nd; q++) wv[q] -= hj * vj[q];
+                }
+                if (ww - c2 > 0.25 * ww) hn = sqrt(ww - c2);
+            }
+            if (hn < 0.0) hn = sqrt(vdot(nd, wv, wv));
             Hk[k + 1] = hn;
             double* vn = V + (long)(k + 1) * nd;
             if (hn > 0.0) {

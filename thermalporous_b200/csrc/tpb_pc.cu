@@ -435,6 +435,23 @@ __global__ void __launch_bounds__(256) strength_kernel(const double* __restrict_
     }
 }
 
+// Row repair of a scalar operator before it is handed to the multigrid.  Newton iterates may leave the physical
+// range for a few cells (S_o < 0 at an injector, S_o > 1: basic line search, thermalmodel.py:165), which gives
+// the pressure row of those cells negative mobilities: positive off-diagonals and a diagonal that is negative or
+// far from dominant.  Gauss-Seidel amplifies on such rows and the V-cycle stops being a contraction (measured: a
+// 200-iteration FGMRES stall with 5 such rows out of 4.5 M).  A diagonal below 0.8 x the sum of the row's
+// |couplings| is raised to that sum; every other row is left bit-for-bit alone, and only the preconditioner's copy
+// of the operator is touched.
+template <int NS>
+__global__ void __launch_bounds__(256) row_repair_kernel(double* __restrict__ a, long long n) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double sum = 0.0;
+#pragma unroll
+    for (int s = 1; s < NS; s++) sum += fabs(a[(long long)s * n + c]);
+    if (a[c] < 0.8 * sum) a[c] = sum;
+}
+
 // Galerkin coarse operator for piecewise-constant aggregates (stays a 5|7-point stencil)
 template <int NS>
 __global__ void __launch_bounds__(128) coarsen_op_kernel(const double* __restrict__ af, LevGeom f, LevGeom cg,
@@ -1024,6 +1041,8 @@ void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
     const bool dist = nranks > 1;
     std::vector<int> planes;
     if (dist) planes = tpb_comm_planes(h);
+    row_repair_kernel<NS><<<nblk(h->g.n, 256), 256, 0, h->stream>>>(a0, h->g.n);
+    h->launches++;
     mg_coarsen_t<NS>(h, m, a0, h->g.nx, h->g.ny, h->g.nz, dist, planes);
     if (!dist) return;
     // ---- gather level: concatenate the ranks' last levels along the slab axis ----------------------
