@@ -38,7 +38,7 @@ CPU_SAMPLE_NZ = 17
 
 
 def workload_name(nz, mult, mode="stack"):
-    how = "" if mult == 1 else (", %d stacked copies of the 85-layer column" % mult if mode == "stack" else ", z-refined x%d" % mult)
+    how = "" if mult == 1 else (", %d stacked copies of the 85-layer reservoir, each with its own well pair" % mult if mode == "stack" else ", z-refined x%d" % mult)
     return ("SPE10-shaped synthetic 60x220x%d (seed 10%s) TwoPhase thermal, wells 'default' Peaceman rate 2e-4, "
             "S_o=0.9, %s, small_dt_start 2^-10 of maxdt=1 day" % (nz, how, PC))
 
@@ -204,8 +204,15 @@ def run_b200(args):
     geo = make_geo(prm, NZ, refine, args.scale)      # global grid 60 x 220 x 85*world
     from thermalporous_b200.partition import Slab
     slab = Slab(geo, world, rank)
-    case = CS.WellCase(prm, geo, well_case="default")
-    ent = slab.localize_sources(CS.source_entries(case, prm, geo))
+    if refine > 1 and args.scale == "stack":
+        # every stacked copy of the reservoir keeps its own producer/injector pair (the wells of the N=1 case at the
+        # same place inside each copy), so each rank's slab is the N=1 problem coupled to its neighbours
+        base = make_geo(prm, NZ, 1)
+        base_ent = CS.source_entries(CS.WellCase(prm, base, well_case="default"), prm, base)
+        all_ent = [(c + r * base.ncell,) + tuple(rest) for r in range(refine) for (c, *rest) in base_ent]
+    else:
+        all_ent = CS.source_entries(CS.WellCase(prm, geo, well_case="default"), prm, geo)
+    ent = slab.localize_sources(all_ent)
     nxl, nyl, nzl = slab.local_dims()
     eng = Engine(3, nxl, nyl, nzl, geo.Dx, geo.Dy, geo.Dz, 2, prm, device=local, has_lo=slab.has_lo, has_hi=slab.has_hi)
     for fid, arr in ((L.TPB_PHI, geo.phi), (L.TPB_KX, geo.K_x), (L.TPB_KY, geo.K_y), (L.TPB_KZ, geo.K_z)):
