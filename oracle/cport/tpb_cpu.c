@@ -689,6 +689,9 @@ static void mg_restrict(const mglevel* f, const mglevel* c, const double* r, dou
                 for (int di = 0; di < f->cx; di++) {
                     int i = I * f->cx + di, j = Jc * f->cy + dj, k = Kc * f->cz + dk;
                     if (i >= f->nx || j >= f->ny || k >= f->nz) continue;
+                    /* the pre-smoothing sweep ended on colour 1: those rows were just solved, their residual is
+                     * zero and is not summed (csrc/tpb_pc.cu restrict_cell) */
+                    if ((i + j + k) & 1) continue;
                     acc += r[i + (long)f->nx * (j + (long)f->ny * k)];
                 }
         bc[C] = acc;

@@ -101,6 +101,29 @@ def test_c3_two_phase_spe10_slice(pc):
     assert 0.0 <= S.min() and S.max() <= 1.0 and len(res.dt_vec) >= 3
 
 
+def test_mixing_case_initial_condition_and_field_output(tmp_path, monkeypatch):
+    """mixingcase.py "coldandhot": no sources, hot / cold halves as initial condition (thermalmodel.py:23-26), fields
+    written every n_save-th step as the reference's save=True does (:113-133, 304-320)."""
+    from thermalporous_b200 import vtkout
+    monkeypatch.chdir(tmp_path)
+    prm = params(S_o=0.9)
+    geo = G.HomogeneousGeo(24, 20, prm, 20.0, 20.0)
+    case = CS.MixingCase(prm, geo, "coldandhot")
+    model = TwoPhase(geo, case, prm, end=0.03, maxdt=0.01, small_dt_start=False, solver_parameters="pc_cptr",
+                     verbosity=False, save=True, n_save=2)
+    ic = model.initial_condition
+    assert set(np.unique(ic[1])) == {prm.T_prod, prm.T_inj} and (ic[2] == 0.9).all()
+    res = check(model, 2, "pc_cptr")
+    p, T, S = model.fields()
+    assert prm.T_prod < T.mean() < prm.T_inj and T.max() - T.min() < prm.T_inj - prm.T_prod + 1e-9
+    # initial state + steps 1 and 3 (i_plot 0 and 2)
+    nsaved = 1 + len([k for k in range(len(res.dt_vec)) if k % 2 == 0])
+    for name in ("pressure", "temperature", "saturation_o"):
+        assert (tmp_path / "results" / (name + ".pvd")).read_text().count("<DataSet") == nsaved
+    ext, sp, arr = vtkout.read_vti(str(tmp_path / "results" / ("temperature_%d.vti" % (nsaved - 1))))
+    assert ext == (0, 24, 0, 20, 0, 1) and arr["temperature"].shape == (geo.ncell,)
+
+
 def test_unsupported_option_set_is_loud():
     prm = params(S_o=0.9)
     geo = G.HomogeneousGeo(8, 8, prm, 20.0, 20.0)

@@ -93,9 +93,9 @@ def test_pc_components_match_cpu_restatement(nphase, dim, shape, opts):
 @pytest.mark.parametrize("nphase,dim,shape,opts", [COMBOS[1], COMBOS[4], COMBOS[9], COMBOS[11], COMBOS[14]])
 @pytest.mark.parametrize("ksp_type", [cport.KSP_GMRES, cport.KSP_FGMRES])
 def test_ksp_matches_cpu_restatement(nphase, dim, shape, opts, ksp_type):
-    # unrefined classical Gram-Schmidt (PETSc's default, restated on both sides) stalls after ~8 decades
-    # on the slowly converging ILU-only case, so that one is solved to 1e-7
-    rtol = 1e-7 if opts.get("stage1") == cport.S1_NONE else 1e-10
+    # classical Gram-Schmidt with a second pass once the residual is below 1e-3 (both sides): unrefined CGS
+    # used to stall after ~8 decades on the slowly converging ILU-only case
+    rtol = 1e-10
     pb, u, uo, g, c = _pair(nphase, dim, shape, dict(opts, ksp_type=ksp_type, ksp_rtol=rtol), seed=4)
     dt = 4000.0
     F, J = g.assemble(u, uo, dt)
@@ -138,6 +138,38 @@ def test_zero_permeability_cells_and_sources_in_the_solver():
     xc, its_c, reason_c, _ = c.ksp_solve(Jc, Fc)
     assert reason_g == reason_c == 2 and abs(its_g - its_c) <= 1
     assert rel_err_rows(xg.cpu().numpy(), xc) < 1e-5
+    g.close()
+    c.close()
+
+
+def test_saturation_outside_0_1_does_not_break_the_preconditioner():
+    """Newton iterates may leave [0,1] (basic line search): S_o > 1 gives the water phase a negative mobility and
+    the pressure rows of those cells lose diagonal dominance.  The multigrid's row repair keeps the V-cycle a
+    contraction; both sides repair the same rows and the Krylov solve still converges to 1e-8."""
+    pb, u, uo = random_problem(3, 2, (10, 12, 14), seed=21, spread=0.02, nsrc=3)
+    rng = np.random.default_rng(3)
+    bad = rng.choice(pb.grid.n, size=12, replace=False)
+    u[2, bad[:8]] = 1.0 + rng.uniform(0.005, 0.05, 8)
+    u[2, bad[8:]] = -rng.uniform(0.005, 0.03, 4)
+    g = engine_from_problem(pb)
+    c = cport.engine_from_problem(pb)
+    for e in (g, c):
+        e.set_solver_opts(stage1=cport.S1_CPTR, decoup=0, ksp_rtol=1e-8)
+    dt = 300.0
+    F, J = g.assemble(u, uo, dt)
+    Jh, Fh = J.cpu().numpy(), F.cpu().numpy()
+    g.pc_setup(J, u, dt)
+    c.pc_setup(Jh, u, dt)
+    for which in (0, 1):
+        a_g, a_c = g.mg_level_op(which, 0).cpu().numpy(), c.mg_level_op(which, 0)
+        assert rel_err_rows(a_g, a_c) < TOL
+        assert (a_c[0] >= 0.8 * np.abs(a_c[1:]).sum(axis=0) * (1 - 1e-12)).all()      # every row repaired or healthy
+        b = rng.normal(size=pb.grid.n)
+        yg, yc = g.mg_apply(which, b).cpu().numpy(), c.mg_apply(which, b)
+        assert np.isfinite(yg).all() and np.abs(yg - yc).max() < 1e-9 * np.abs(yc).max()
+    xg, its_g, reason_g, _ = g.ksp_solve(J, F)
+    xc, its_c, reason_c, _ = c.ksp_solve(Jh, Fh)
+    assert reason_g == reason_c == 2 and abs(its_g - its_c) <= 1 and its_g < 80
     g.close()
     c.close()
 

@@ -177,3 +177,60 @@ def test_checkpoint_round_trip(tmp_path):
     assert np.array_equal(load_checkpoint(str(tmp_path / "chk"), (3, 40)), u)
     with pytest.raises(ValueError):
         load_checkpoint(str(tmp_path / "chk"), (2, 40))
+
+
+def test_mixing_case_initial_conditions():
+    """mixingcase.py:20-47."""
+    from thermalporous_b200 import cases as CS, geo as G
+    from thermalporous_b200.physicalparameters import PhysicalParameters
+    prm = PhysicalParameters()
+    g2 = G.HomogeneousGeo(6, 8, prm, 12.0, 16.0)
+    ic = CS.MixingCase(prm, g2, "coldandhot").init_IC("Single phase")
+    T = ic[1].reshape(8, 6)
+    assert ic.shape == (2, 48) and (T[:4] == prm.T_inj).all() and (T[4:] == prm.T_prod).all() and (ic[0] == prm.p_ref).all()
+    assert CS.MixingCase(prm, g2, "coldonhot").mixing_case == "coldandhot"        # 2-D falls back (mixingcase.py:13-15)
+    g3 = G.HomogeneousBoxGeo(3, 4, 6, prm, 6.0, 8.0, 12.0)
+    ic3 = CS.MixingCase(prm, g3, "coldonhot").init_IC("Two-phase")
+    T3 = ic3[1].reshape(6, 4, 3)
+    assert ic3.shape == (3, 72) and (T3[:3] == prm.T_inj).all() and (T3[3:] == prm.T_prod).all() and (ic3[2] == prm.S_o).all()
+    prm2 = PhysicalParameters()
+    hl = CS.MixingCase(prm2, g3, "heavyonlight")
+    assert prm2.API == 40
+    S = hl.init_IC("Two-phase")[2].reshape(6, 4, 3)
+    assert (S[:3] == 1.0).all() and (S[3:] == 0.0).all()
+    with pytest.raises(SystemExit):
+        hl.init_IC("Single phase")
+    with pytest.raises(SystemExit):
+        CS.MixingCase(prm, g3, "sideways")
+
+
+def test_vti_pvd_output_and_matlab_dumps(tmp_path):
+    """save=True writer (thermalmodel.py:113-133) and the utils.ExportJacobian / ExportResidual dump format
+    (utils.py:27-43) with its loader: the loaded sparse matrix acts like the block-stencil SpMV."""
+    from oracle import tp_oracle as orc
+    from thermalporous_b200 import geo as G, vtkout as V
+    from thermalporous_b200.partition import Slab
+    from thermalporous_b200.physicalparameters import PhysicalParameters
+    prm = PhysicalParameters()
+    g = G.HomogeneousBoxGeo(4, 3, 5, prm, 10.0, 10.0, 10.0)
+    rng = np.random.default_rng(0)
+    for world, rank in ((1, 0), (2, 1)):
+        sl = Slab(g, world, rank)
+        w = V.PvdWriter(str(tmp_path / ("w%d" % world)), ["pressure", "temperature"], g, sl, "" if world == 1 else "_rank1of2")
+        f = rng.random((2, sl.ncell))
+        w.write(0.0, f)
+        w.write(0.5, 2 * f)
+        w.close()
+        suffix = "" if world == 1 else "_rank1of2"
+        ext, sp, arr = V.read_vti(str(tmp_path / ("w%d" % world) / ("pressure%s_1.vti" % suffix)))
+        assert ext == (0, 4, 0, 3, sl.k0, sl.k1) and sp == (g.Dx, g.Dy, g.Dz)
+        assert np.array_equal(arr["pressure"], 2 * f[0])
+        assert (tmp_path / ("w%d" % world) / ("temperature%s.pvd" % suffix)).read_text().count("<DataSet") == 2
+    J = rng.normal(size=(7, 3, 3, g.ncell))
+    V.export_jacobian(J, 4, 3, 5, str(tmp_path / "matrix.txt"))
+    A = V.load_matlab_matrix(str(tmp_path / "matrix.txt"))
+    x = rng.normal(size=(3, g.ncell))
+    y = orc.spmv(J, orc.Grid(4, 3, 5, 1.0, 1.0, 1.0, 3), x)
+    assert A.shape == (3 * g.ncell, 3 * g.ncell) and np.abs(A @ x.reshape(-1) - y.reshape(-1)).max() < 1e-13
+    V.export_residual(x, str(tmp_path / "rhs.txt"))
+    assert np.array_equal(V.load_matlab_vector(str(tmp_path / "rhs.txt")), x.reshape(-1))

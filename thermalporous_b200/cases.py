@@ -232,6 +232,45 @@ class SourceTerms(_CaseBase):
         return out
 
 
+class MixingCase:
+    """mixingcase.py:3-47: no sources, a non-uniform initial condition (`init_IC`) instead - cold/hot halves in y
+    ("coldandhot") or z ("coldonhot", 3-D only), or oil over water in the upper/lower half ("heavyonlight",
+    two-phase only; sets API = 40).  `init_IC` returns the (nf, ncell) field array in the C-ABI cell order."""
+
+    def __init__(self, params, geo, mixing_case="coldandhot"):
+        self.name = "Mixing"
+        self.geo, self.params, self.mixing_case = geo, params, mixing_case
+        if mixing_case not in ("coldonhot", "coldandhot", "heavyonlight"):
+            raise SystemExit("Error: Undefined mixing_case: %s" % mixing_case)                  # mixingcase.py:11-12
+        if mixing_case == "coldonhot" and geo.dim == 2:
+            print("Warning: coldonhot only implemented for 3D cases. Switching to coldandhot")  # :13-15
+            self.mixing_case = "coldandhot"
+        if mixing_case == "heavyonlight":
+            self.params.API = 40                                                               # :16-18
+
+    def init_IC(self, phases="Single phase"):
+        geo, prm = self.geo, self.params
+        cc = geo.cell_centres()
+        n = geo.ncell
+        p = np.full(n, float(prm.p_ref))
+        T = np.full(n, float(prm.T_prod))
+        S = None
+        if self.mixing_case == "coldandhot":                                                   # :27-30
+            T = np.where(cc[:, 1] > geo.Length_y / 2.0, prm.T_prod, prm.T_inj).astype(np.float64)
+        elif self.mixing_case == "coldonhot":                                                  # :31-34
+            T = np.where(cc[:, 2] > geo.Length_z / 2.0, prm.T_prod, prm.T_inj).astype(np.float64)
+        else:                                                                                  # :35-43
+            if phases == "Single phase":
+                raise SystemExit("Error: heavyonlight case not defined for Single Phase")
+            ax, half = (1, geo.Length_y / 2.0) if geo.dim == 2 else (2, geo.Length_z / 2.0)
+            S = np.where(cc[:, ax] > half, 0.0, 1.0)
+        if phases == "Two-phase":
+            if S is None:
+                S = np.full(n, float(prm.S_o))                                                 # :44-46
+            return np.stack([p, T, S])
+        return np.stack([p, T])
+
+
 def source_entries(case, params, geo):
     """Flatten a case into libtpb200 source records (cell, kind, weight, bhp, max_rate, const_rate)."""
     V = geo.cell_volume

@@ -536,8 +536,10 @@ __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a,
 }
 
 // bc[C] = sum over the aggregate of (b - A x)  (residual + restriction fused).  The aggregate is walked as a
-// fully unrolled 2x2x2 box with predication so that the loads of all its fine cells are in flight together;
-// the summation order (k, j, i; within a cell diag, x-, x+, ...) is the one the CPU restatement uses.
+// fully unrolled 2x2x2 box; the summation order (k, j, i; within a cell diag, x-, x+, ...) is the one the CPU
+// restatement uses.
+// Only the cells of colour 0 contribute: the restriction always follows a pre-smoothing sweep whose last pass
+// updated colour 1, and a Gauss-Seidel update leaves a zero residual in the row it solved - half of the loads.
 template <int NS>
 __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, const double* b, const double* x,
                                                 const LevGeom& f, int I, int Jc, int Kc) {
@@ -545,22 +547,21 @@ __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, co
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
-        int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
-        const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz;
-        // an absent member of the aggregate is evaluated at the aggregate's first cell and discarded
-        i = ok ? i : I * f.cx;
-        j = ok ? j : Jc * f.cy;
-        k = ok ? k : Kc * f.cz;
-        long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
-        double acc = b[c] - a[c] * x[c];
+        const int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
+        const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + k) & 1) == 0;
+        r[q] = 0.0;
+        if (ok) {
+            long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
+            double acc = b[c] - a[c] * x[c];
 #pragma unroll
-        for (int s = 1; s < NS; s++) {
-            bool ex;
-            long long nb = nbr_clamped(f.nx, f.ny, f.nz, i, j, k, c, s, ex);
-            double p = a[(long long)s * f.n + c] * x[nb];
-            acc -= ex ? p : 0.0;
+            for (int s = 1; s < NS; s++) {
+                bool ex;
+                long long nb = nbr_clamped(f.nx, f.ny, f.nz, i, j, k, c, s, ex);
+                double p = a[(long long)s * f.n + c] * x[nb];
+                acc -= ex ? p : 0.0;
+            }
+            r[q] = acc;
         }
-        r[q] = ok ? acc : 0.0;
     }
     double sum = 0.0;
 #pragma unroll
@@ -568,15 +569,42 @@ __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, co
     return sum;
 }
 
+// One thread per FINE cell of the aggregate box (8 lanes per coarse cell): each thread has one row's 2*NS loads in
+// flight instead of eight rows' one after the other (measured: 13 us -> latency of one row on the small levels);
+// lane 0 of the group then adds the eight residuals in the fixed order q = 0..7 of restrict_cell.
 template <int NS>
-__global__ void __launch_bounds__(128) restrict_kernel(const double* __restrict__ a, const double* __restrict__ b,
+__global__ void __launch_bounds__(256) restrict_kernel(const double* __restrict__ a, const double* __restrict__ b,
                                                        const double* __restrict__ x, LevGeom f, LevGeom cg,
                                                        double* __restrict__ bc) {
-    long long C = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (C >= cg.n) return;
-    int I, Jc, Kc;
-    tpb_ijk(C, cg.nx, cg.ny, I, Jc, Kc);
-    bc[C] = restrict_cell<NS>(a, b, x, f, I, Jc, Kc);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long C = t >> 3;
+    const int q = (int)(t & 7);
+    double r = 0.0;
+    if (C < cg.n) {
+        int I, Jc, Kc;
+        tpb_ijk(C, cg.nx, cg.ny, I, Jc, Kc);
+        const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
+        const int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
+        const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + k) & 1) == 0;
+        if (ok) {
+            long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
+            double acc = b[c] - a[c] * x[c];
+#pragma unroll
+            for (int s = 1; s < NS; s++) {
+                bool ex;
+                long long nb = nbr_clamped(f.nx, f.ny, f.nz, i, j, k, c, s, ex);
+                double p = a[(long long)s * f.n + c] * x[nb];
+                acc -= ex ? p : 0.0;
+            }
+            r = acc;
+        }
+    }
+    // whole warps reach this point (the grid is padded to full blocks)
+    const int base = (threadIdx.x & 31) & ~7;
+    double sum = 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; m++) sum += __shfl_sync(0xffffffffu, r, base + m);
+    if (q == 0 && C < cg.n) bc[C] = sum;
 }
 
 __global__ void __launch_bounds__(256) prolong_add_kernel(const double* __restrict__ xc, LevGeom f, LevGeom cg,
@@ -1137,7 +1165,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         }
         for (int s = 0; s < pre; s++) mg_rbgs<NS>(h, L, s == 0);
         MgLevel& Cc = m.lev[l + 1];
-        restrict_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
+        restrict_kernel<NS><<<nblk(Cc.n * 8, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
         h->launches++;
     }
     if (!dist) {

@@ -50,7 +50,7 @@ class LoopResult:
 
 
 def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_fact, two_phase, i_S, spe10,
-                  verbose=False, log=print, max_steps=None, dt0=None):
+                  verbose=False, log=print, max_steps=None, dt0=None, after_step=None):
     """thermalmodel.py:97-348.  `newton(u, u_old, dt)` solves one step in place and returns an object with
     .nits .lits .reason (raises nothing); `ops` gives copy(dst, src), minmax(u, f) and clip(u, f, lo, hi).
     Times are in seconds except `end`/`maxdt` (days, as in the reference)."""
@@ -116,6 +116,8 @@ def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_
         res.nits_vec.append(st.nits)                             # :327-336
         res.lits_vec.append(st.lits)
         res.stats.append(st)
+        if after_step is not None:
+            after_step(t)
         if verbose:
             log("Nonlinear iterations: %d\nLinear iterations: %d" % (st.nits, st.lits))
         current_dt = dt
@@ -168,8 +170,9 @@ class ThermalModel:
                  filename="results/results.txt", dt_init_fact=2 ** (-10), verbosity=True, device=0):
         from .engine import Engine
         from . import _lib as L
-        if save:
-            raise NotImplementedError("pvd/VTK output is outside the hot path (SURVEY.md 8f)")
+        # thermalmodel.py:113-133,304-320: every n_save-th step the fields go to results/<field>.pvd; here a .pvd
+        # collection of VTK ImageData (.vti) files per field, written by rank 0's slab owner for its own slab
+        self.save, self.n_save = bool(save), int(n_save)
         # thermalmodel.py:20-21; the reference stores the solution with DumbCheckpoint (HDF5) - here a .npz of
         # the fields in the C-ABI cell order
         self.checkpointing = {"save": False, "load": False, "savename": "initial", "loadname": "initial"}
@@ -208,7 +211,11 @@ class ThermalModel:
             e.comm_init(uid[0], self.rank, self.world)
             e.exchange_static()
         e.set_solver_opts(**self.solver_opts)
-        self.initial_condition = slab.take(self.init_IC_uniform())      # this rank's part
+        try:                                                             # thermalmodel.py:23-26
+            ic = self.case.init_IC(phases=self.name)
+        except AttributeError:
+            ic = self.init_IC_uniform()
+        self.initial_condition = slab.take(ic)                           # this rank's part
         self.u = e.tensor(self.initial_condition)
         self.u_ = self.u.clone()
         self.total_nits = self.total_lits = 0
@@ -230,11 +237,27 @@ class ThermalModel:
         else:
             self.u.copy_(e.tensor(self.initial_condition))
         self.u_.copy_(self.u)
+        writer = None
+        if self.save:
+            from .vtkout import PvdWriter
+            names = ["pressure", "temperature"] + (["saturation_o"] if self.nphase == 2 else [])   # :113-133
+            writer = PvdWriter("results", names, self.geo, self.slab, self._rank_suffix())
+            writer.write(0.0, self.fields())
+        state = {"i_plot": 0}
+
+        def after_step(t):
+            if writer is not None:                                       # thermalmodel.py:304-320
+                if state["i_plot"] % self.n_save == 0:
+                    writer.write(t, self.fields())
+                state["i_plot"] += 1
+
         res = run_time_loop(lambda u, uo, dt: e.newton_solve(u, uo, dt), _TorchOps(e), self.u, self.u_,
                             end=self.end, maxdt=self.maxdt, small_dt_start=self.small_dt_start,
                             dt_init_fact=self.dt_init_fact, two_phase=self.nphase == 2, i_S=2,
                             spe10=self.geo.name.startswith("SPE10"), verbose=self.verbosity and self.rank == 0,
-                            max_steps=max_steps)
+                            max_steps=max_steps, after_step=after_step)
+        if writer is not None:
+            writer.close()
         self.result = res
         self.total_nits, self.total_lits = res.total_nits, res.total_lits
         self.last_dt = res.dt_vec[-1] if res.dt_vec else None
