@@ -88,7 +88,10 @@ enum tpb_decoup { TPB_DECOUP_NO = 0, TPB_DECOUP_QI = 1, TPB_DECOUP_TI = 2,
                   TPB_DECOUP_QI_TEMP = 3, TPB_DECOUP_TI_TEMP = 4 };
 enum tpb_schur_pre { TPB_SCHUR_CONVDIFF = 0,  /* ConvDiffSchur(TwoPhases)PC, preconditioners.py:11-333 */
                      TPB_SCHUR_A11 = 1,       /* pc_fieldsplit_schur_precondition a11 */
-                     TPB_SCHUR_DIAG = 2 };    /* pc_fieldsplit_diag: additive, no coupling */
+                     TPB_SCHUR_DIAG = 2,      /* pc_fieldsplit_diag: additive, no coupling */
+                     TPB_SCHUR_SELFP = 3 };   /* pc_fieldsplit_schur_precondition selfp (singlephase.py:322-329):
+                                                 A11 - A10 diag(A00)^-1 A01 collapsed onto the 5|7-point stencil
+                                                 (products that leave the stencil are lumped into the diagonal) */
 enum tpb_stage2 { TPB_S2_NONE = 0, TPB_S2_ILU0 = 1, TPB_S2_BJACOBI = 2 /* per-cell block Jacobi */ };
 
 typedef struct {

@@ -23,7 +23,7 @@ PROD, INJ, HEATER = 0, 1, 2
 KSP_GMRES, KSP_FGMRES = 0, 1
 S1_NONE, S1_CPR, S1_CPTR, S1_FIELDSPLIT = 0, 1, 2, 3
 DECOUP = {"No": 0, "QI": 1, "TI": 2, "QI_temp": 3, "TI_temp": 4}
-SCHUR_CONVDIFF, SCHUR_A11, SCHUR_DIAG = 0, 1, 2
+SCHUR_CONVDIFF, SCHUR_A11, SCHUR_DIAG, SCHUR_SELFP = 0, 1, 2, 3
 S2_NONE, S2_ILU0, S2_BJACOBI = 0, 1, 2
 
 

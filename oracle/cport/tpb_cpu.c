@@ -933,6 +933,28 @@ static void stage1_setup(tpc_handle_s* h, const double* J, const double* u, doub
                 }
     }
     if (o->schur_pre == TPB_SCHUR_CONVDIFF) assemble_convdiff(h, u, dt, h->AT);
+    if (o->schur_pre == TPB_SCHUR_SELFP) {
+        /* AT = A11 - A10 diag(A00)^-1 A01 collapsed onto the stencil (csrc/tpb_pc.cu selfp_kernel) */
+#pragma omp parallel for schedule(static)
+        for (long c = 0; c < n; c++) {
+            int i = (int)(c % g->nx), j = (int)((c / g->nx) % g->ny), k = (int)(c / ((long)g->nx * g->ny));
+            double sub[NSMAX] = {0, 0, 0, 0, 0, 0, 0};
+            for (int s1 = 0; s1 < ns; s1++) {
+                long nb = nbr(g->nx, g->ny, g->nz, i, j, k, s1);
+                if (nb < 0) continue;
+                const double d = h->A00[nb];
+                const double f = d != 0.0 ? h->A00[((long)(s1 * 2 + 1) * 2 + 0) * n + c] / d : 0.0;
+                int i2 = (int)(nb % g->nx), j2 = (int)((nb / g->nx) % g->ny), k2 = (int)(nb / ((long)g->nx * g->ny));
+                for (int s2 = 0; s2 < ns; s2++) {
+                    if (nbr(g->nx, g->ny, g->nz, i2, j2, k2, s2) < 0) continue;
+                    const double v = f * h->A00[((long)(s2 * 2 + 0) * 2 + 1) * n + nb];
+                    const int slot = s1 == 0 ? s2 : (s2 == 0 ? s1 : 0);
+                    sub[slot] += v;
+                }
+            }
+            for (int s = 0; s < ns; s++) h->AT[(long)s * n + c] -= sub[s];
+        }
+    }
     mg_setup(h, &h->mg_p, h->App);
     mg_setup(h, &h->mg_T, h->AT);
 }

@@ -65,7 +65,7 @@ def check(model, nphase, pc):
     return res
 
 
-@pytest.mark.parametrize("pc", ["pc_fieldsplit_cd", "pc_cpr", None])
+@pytest.mark.parametrize("pc", ["pc_fieldsplit_cd", "pc_fieldsplit_selfp", "pc_cpr", None])
 def test_c1_single_phase_homogeneous_wells(pc):
     """tests/test_homo_wells.py: N x N homogeneous box, L = 20 m, wells 'test0' at constant rate, 2 steps of 1 day."""
     prm = params(rate=1e-6, T_prod=320.0)
@@ -95,7 +95,7 @@ def test_c3_two_phase_spe10_slice(pc):
     geo = G.SPE10Model(60, 120, prm, fields=G.spe10_synthetic_layer(60, 120))
     case = CS.WellCase(prm, geo, well_case="SPE10_60x120")
     model = TwoPhase(geo, case, prm, end=0.004, maxdt=0.002, small_dt_start=True, dt_init_fact=2 ** -4,
-                     solver_parameters=pc, verbosity=False)
+                     solver_parameters=pc, verbosity=False, vector=(pc == "pc_cpr_TI"))   # vector: layout only
     res = check(model, 2, pc)
     p, T, S = model.fields()
     assert 0.0 <= S.min() and S.max() <= 1.0 and len(res.dt_vec) >= 3

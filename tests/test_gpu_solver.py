@@ -29,6 +29,9 @@ COMBOS = [
     (1, 2, (1, 16, 23), dict(stage1=cport.S1_FIELDSPLIT, schur_pre=cport.SCHUR_CONVDIFF, stage2=cport.S2_NONE)),
     (1, 3, (5, 8, 9), dict(stage1=cport.S1_FIELDSPLIT, schur_pre=cport.SCHUR_A11, stage2=cport.S2_NONE)),
     (1, 2, (1, 12, 15), dict(stage1=cport.S1_FIELDSPLIT, schur_pre=cport.SCHUR_DIAG, stage2=cport.S2_NONE)),
+    (1, 2, (1, 14, 19), dict(stage1=cport.S1_FIELDSPLIT, schur_pre=cport.SCHUR_SELFP, stage2=cport.S2_NONE)),
+    (1, 3, (6, 7, 8), dict(stage1=cport.S1_FIELDSPLIT, schur_pre=cport.SCHUR_SELFP, stage2=cport.S2_NONE)),
+    (2, 3, (5, 6, 9), dict(stage1=cport.S1_CPTR, decoup=1, schur_pre=cport.SCHUR_SELFP)),
     (2, 3, (4, 6, 40), dict(stage1=cport.S1_NONE, stage2=cport.S2_ILU0)),
     (2, 3, (4, 6, 10), dict(stage1=cport.S1_CPR, stage2=cport.S2_BJACOBI)),
     (2, 3, (20, 24, 40), dict(stage1=cport.S1_CPTR, decoup=1, mg_pre=2, mg_post=2, mg_cycles=2)),

@@ -93,8 +93,11 @@ def test_option_sets_resolve_like_the_reference_dispatchers():
     for bad in ("pc_lu", "pc_hypre", "pc_cptramg", "faspardecomp"):
         with pytest.raises(O.UnsupportedOption):
             O.resolve(bad, 2)
-    with pytest.raises(O.UnsupportedOption):
-        O.resolve("pc_fieldsplit_selfp", 1)
+    o, _, _ = O.resolve("pc_fieldsplit_selfp", 1)      # singlephase.py:322-329
+    assert (o["stage1"], o["schur_pre"], o["stage2"]) == (O.S1_FIELDSPLIT, O.SCHUR_SELFP, O.S2_NONE)
+    o, _, _ = O.resolve({"pc_type": "fieldsplit", "pc_fieldsplit_type": "schur", "pc_fieldsplit_schur_fact_type": "FULL",
+                         "pc_fieldsplit_schur_precondition": "selfp"}, 1)
+    assert o["schur_pre"] == O.SCHUR_SELFP
     # the raw PETSc dict the reference's pc_cptr expands to (twophase.py:531-550) plus a decoupling key
     v_cycle = {"ksp_type": "preonly", "pc_type": "hypre", "pc_hypre_type": "boomeramg", "pc_hypre_boomeramg_max_iter": 1}
     d = {"snes_type": "newtonls", "snes_max_it": 25, "ksp_type": "fgmres", "ksp_max_it": 200, "ksp_gmres_restart": 200,

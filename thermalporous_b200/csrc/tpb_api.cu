@@ -328,6 +328,7 @@ int tpb_set_solver_opts(tpb_handle h, const tpb_solver_opts* o) {
     TPB_REQUIRE(h && o, TPB_ERR_ARG, "null argument");
     TPB_REQUIRE(o->ksp_restart > 0 && o->ksp_max_it >= 0 && o->snes_max_it >= 0, TPB_ERR_ARG, "bad iteration limits");
     TPB_REQUIRE(o->stage1 >= 0 && o->stage1 <= 3 && o->stage2 >= 0 && o->stage2 <= 2, TPB_ERR_ARG, "bad PC stage");
+    TPB_REQUIRE(o->schur_pre >= 0 && o->schur_pre <= 3 && o->decoup >= 0 && o->decoup <= 4, TPB_ERR_ARG, "bad PC option");
     TPB_REQUIRE(!(o->stage1 == TPB_S1_CPTR && h->nphase == 1), TPB_ERR_UNSUPPORTED,
                 "CPTR needs the two-phase model (preconditioners.py:1258-1267)");
     TPB_REQUIRE(!(o->stage1 == TPB_S1_FIELDSPLIT && h->nphase == 2), TPB_ERR_UNSUPPORTED,

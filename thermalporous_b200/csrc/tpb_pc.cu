@@ -788,6 +788,42 @@ __global__ void __launch_bounds__(256) a00_sub_kernel(const double* __restrict__
     r[c] -= acc;
 }
 
+// selfp Schur approximation (PETSc pc_fieldsplit_schur_precondition selfp, singlephase.py:322-329):
+// AT = A11 - A10 diag(A00)^-1 A01, kept on the 5|7-point stencil: a product A10[s1] * A01[s2] lands on slot s2 when
+// s1 is the diagonal, on slot s1 when s2 is, on the diagonal when s2 leads back to the row's cell, and is lumped
+// into the diagonal otherwise (two steps away: outside the stencil).  AT holds A11 on entry.
+template <int DIM>
+__global__ void __launch_bounds__(128) selfp_kernel(const double* __restrict__ A00, Geom g, double* __restrict__ AT) {
+    const long long n = g.n;
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    constexpr int NS = 2 * DIM + 1;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    int i, j, k;
+    tpb_ijk(c, nx, ny, i, j, k);
+    double sub[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) sub[s] = 0.0;
+#pragma unroll
+    for (int s1 = 0; s1 < NS; s1++) {
+        long long nb = nbr_cell(nx, ny, nz, i, j, k, c, s1);
+        if (nb < 0) continue;
+        const double d = A00[nb];   // (s=0, a=0, b=0) of the neighbour
+        const double f = d != 0.0 ? A00[((long long)(s1 * 2 + 1) * 2 + 0) * n + c] / d : 0.0;
+        int i2, j2, k2;
+        tpb_ijk(nb, nx, ny, i2, j2, k2);
+#pragma unroll
+        for (int s2 = 0; s2 < NS; s2++) {
+            if (nbr_cell(nx, ny, nz, i2, j2, k2, nb, s2) < 0) continue;
+            const double v = f * A00[((long long)(s2 * 2 + 0) * 2 + 1) * n + nb];
+            const int slot = s1 == 0 ? s2 : (s2 == 0 ? s1 : 0);
+            sub[slot] += v;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) AT[(long long)s * n + c] -= sub[s];
+}
+
 // ---- K8: red-black block ILU(0) --------------------------------------------------------------------
 template <int NF, int DIM>
 __global__ void __launch_bounds__(128) ilu_setup_kernel(const double* __restrict__ J, Geom g, int col, int ilu,
@@ -1281,6 +1317,10 @@ void stage1_setup_t(tpb_handle_s* h, const double* J, const double* u, double dt
                 h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u, h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, pc->AT);
             h->launches++;
         }
+    }
+    if (o.schur_pre == TPB_SCHUR_SELFP) {
+        selfp_kernel<DIM><<<nblk(n, 128), 128, 0, h->stream>>>(pc->A00, h->g, pc->AT);
+        h->launches++;
     }
     mg_setup(h, pc->mg_p, pc->App);
     mg_setup(h, pc->mg_T, pc->AT);

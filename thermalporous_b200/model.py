@@ -296,11 +296,13 @@ class SinglePhase(ThermalModel):
                  dt_init_fact=2 ** (-10), vector=False, gravity2D=False, verbosity=True, device=0):
         self.name = "Single phase"
         self.geo, self.case, self.params = geo, case, params
-        if vector:
-            raise NotImplementedError("vector=True (interleaved p,T layout) is not realised; see SURVEY.md 8f rank 3")
+        # vector=True makes (p,T) one VectorFunctionSpace in the reference (interleaved dofs, singlephase.py:16-17,
+        # twophase.py:20-21) so that hypre can treat them as a system; the equations and the solution are the same.
+        # The C-ABI layout is always field-major, so the flag is accepted and only recorded - the option sets that
+        # NEED the interleaved block (pc_cptramg*, pc_cptrlu*) are rejected by options.resolve.
         if gravity2D:
             raise NotImplementedError("gravity2D is orientation-ill-defined on a non-extruded mesh (SURVEY.md appendix 5)")
-        self.vector = False
+        self.vector = bool(vector)
         self.small_dt_start = small_dt_start
         self.solver_parameters = solver_parameters
         self.solver_opts, self.decoup, self.solver_desc = O.resolve(solver_parameters, 1)
@@ -321,11 +323,13 @@ class TwoPhase(ThermalModel):
                  dt_init_fact=2 ** (-10), vector=False, gravity2D=False, verbosity=True, device=0):
         self.name = "Two-phase"
         self.geo, self.case, self.params = geo, case, params
-        if vector:
-            raise NotImplementedError("vector=True (interleaved p,T layout) is not realised; see SURVEY.md 8f rank 3")
+        # vector=True makes (p,T) one VectorFunctionSpace in the reference (interleaved dofs, singlephase.py:16-17,
+        # twophase.py:20-21) so that hypre can treat them as a system; the equations and the solution are the same.
+        # The C-ABI layout is always field-major, so the flag is accepted and only recorded - the option sets that
+        # NEED the interleaved block (pc_cptramg*, pc_cptrlu*) are rejected by options.resolve.
         if gravity2D:
             raise NotImplementedError("gravity2D is orientation-ill-defined on a non-extruded mesh (SURVEY.md appendix 5)")
-        self.vector = False
+        self.vector = bool(vector)
         self.i_S_o = 2
         self.small_dt_start = small_dt_start
         self.solver_parameters = solver_parameters

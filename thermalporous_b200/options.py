@@ -13,7 +13,7 @@ from __future__ import annotations
 KSP_GMRES, KSP_FGMRES = 0, 1
 S1_NONE, S1_CPR, S1_CPTR, S1_FIELDSPLIT = 0, 1, 2, 3
 DECOUP = {"No": 0, "QI": 1, "TI": 2, "QI_temp": 3, "TI_temp": 4}
-SCHUR_CONVDIFF, SCHUR_A11, SCHUR_DIAG = 0, 1, 2
+SCHUR_CONVDIFF, SCHUR_A11, SCHUR_DIAG, SCHUR_SELFP = 0, 1, 2, 3
 S2_NONE, S2_ILU0, S2_BJACOBI = 0, 1, 2
 
 
@@ -36,6 +36,8 @@ def _two_stage(stage1, decoup="No", schur=SCHUR_CONVDIFF, stage2=S2_ILU0):
 SINGLE_PHASE_SETS = {
     # name: (reference lines, options)
     "pc_fieldsplit_cd": ("singlephase.py:309-319", _two_stage(S1_FIELDSPLIT, schur=SCHUR_CONVDIFF, stage2=S2_NONE)),
+    # selfp is formed on the 5|7-point stencil (products that leave it are lumped into the diagonal), include/tpb200.h
+    "pc_fieldsplit_selfp": ("singlephase.py:322-329", _two_stage(S1_FIELDSPLIT, schur=SCHUR_SELFP, stage2=S2_NONE)),
     "pc_fieldsplit_a11": ("singlephase.py:331-338", _two_stage(S1_FIELDSPLIT, schur=SCHUR_A11, stage2=S2_NONE)),
     "pc_fieldsplit_diag": ("singlephase.py:371-375", _two_stage(S1_FIELDSPLIT, schur=SCHUR_DIAG, stage2=S2_NONE)),
     "pc_cpr": ("singlephase.py:341-351", _two_stage(S1_CPR)),
@@ -65,7 +67,6 @@ TWO_PHASE_SETS = {
 }
 
 _UNSUPPORTED = {
-    "pc_fieldsplit_selfp": "selfp Schur approximation A11 - A10 diag(A00)^-1 A01 leaves the 5|7-point stencil",
     "pc_hypre": "system BoomerAMG on the coupled matrix", "pc_amg": "system BoomerAMG", "pc_ml": "ML",
     "pc_lu": "direct solve (MUMPS/PETSc LU)", "pc_mg": "geometric PCMG over a mesh hierarchy",
     "pc_cptramg": "system AMG on the interleaved (p,T) block", "pc_cptramg_QI": "system AMG on (p,T)",
@@ -109,7 +110,8 @@ def _from_dict(d, nphase):
             inner = d.get("sub_0_cpr_stage1_pc_type", "fieldsplit")
             if inner != "fieldsplit":
                 raise UnsupportedOption("CPTR inner PC %r (only the Schur field-split of pc_cptr is realised)" % inner)
-            schur = SCHUR_A11 if d.get("sub_0_cpr_stage1_pc_fieldsplit_schur_precondition") == "a11" else SCHUR_CONVDIFF
+            schur = {"a11": SCHUR_A11, "selfp": SCHUR_SELFP}.get(d.get("sub_0_cpr_stage1_pc_fieldsplit_schur_precondition"),
+                                                                  SCHUR_CONVDIFF)
             o.update(_two_stage(S1_CPTR, d.get("sub_0_cpr_decoup", "No"), schur))
         elif py0.endswith("CPRStage1PC") or py0.endswith("CPRStage1PC_mat"):
             o.update(_two_stage(S1_CPR, d.get("sub_0_cpr_decoup", "No")))
@@ -132,9 +134,7 @@ def _from_dict(d, nphase):
             o.update(_two_stage(S1_FIELDSPLIT, schur=SCHUR_DIAG, stage2=S2_NONE))
         else:
             pre = d.get("pc_fieldsplit_schur_precondition", None)
-            if pre == "selfp":
-                raise UnsupportedOption(_UNSUPPORTED["pc_fieldsplit_selfp"])
-            schur = SCHUR_A11 if pre == "a11" else SCHUR_CONVDIFF
+            schur = {"a11": SCHUR_A11, "selfp": SCHUR_SELFP}.get(pre, SCHUR_CONVDIFF)
             o.update(_two_stage(S1_FIELDSPLIT, schur=schur, stage2=S2_NONE))
     elif pc_type in ("ilu", "bjacobi", None):
         o.update(_two_stage(S1_NONE))
