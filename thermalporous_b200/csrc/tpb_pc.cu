@@ -520,19 +520,65 @@ __device__ __forceinline__ void rbgs_cell(const double* __restrict__ a, const do
     x[c] = d0 != 0.0 ? acc / d0 : 0.0;
 }
 
+// Programmatic dependent launch (sm_90+): the ~190 small kernels of one PC application depend on each other in a
+// chain, and most of a small level's pass is launch latency plus two dependent rounds of loads.  Kernels launched
+// through launch_pdl() may start while their predecessor drains: they decode their cell and load their row of the
+// operator (constant during a solve) first, and only then wait for the predecessor's results (pdl_wait), so one of
+// the two load rounds and the launch overlap the previous pass.  Every thread executes pdl_wait before it exits -
+// a kernel that finished without waiting would let ITS successor overtake the predecessor.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <int NS, bool PROLONG>
-__global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a, const double* __restrict__ b,
+__global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a, const double* b,
                                                    double* x, LevGeom g, int col, int zero_guess,
-                                                   const double* __restrict__ xc, int cnx, int cny, double omega) {
+                                                   const double* xc, int cnx, int cny, double omega) {
     const int nxh = (g.nx + 1) >> 1;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long rows = (long long)g.ny * g.nz;
-    if (t >= rows * nxh) return;
-    int ih, j, k;
-    tpb_ijk(t, nxh, g.ny, ih, j, k);
-    int i = 2 * ih + ((col + j + k) & 1);
-    if (i >= g.nx) return;
-    rbgs_cell<NS, PROLONG>(a, b, x, g, i, j, k, zero_guess != 0, xc, cnx, cny, omega);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = t < (long long)g.ny * g.nz * nxh;
+    int i = 0, j = 0, k = 0;
+    if (active) {
+        int ih;
+        tpb_ijk(t, nxh, g.ny, ih, j, k);
+        i = 2 * ih + ((col + j + k) & 1);
+        active = i < g.nx;
+    }
+    pdl_launch_dependents();
+    const long long c = i + (long long)g.nx * (j + (long long)g.ny * k);
+    double aa[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) aa[s] = 0.0;
+    if (active) {
+        aa[0] = a[c];
+        if (!zero_guess) {
+#pragma unroll
+            for (int s = 1; s < NS; s++) aa[s] = a[(long long)s * g.n + c];
+        }
+    }
+    pdl_wait();
+    if (!active) return;
+    // from here on the arithmetic is rbgs_cell's, in the same order
+    double acc = b[c];
+    if (!zero_guess) {
+        double tt[NS];
+#pragma unroll
+        for (int s = 1; s < NS; s++) {
+            bool ex;
+            long long nb = nbr_clamped(g.nx, g.ny, g.nz, i, j, k, c, s, ex);
+            double xv = x[nb];
+            if (PROLONG) {
+                const int axis = (s - 1) >> 1, d = ((s - 1) & 1) ? 1 : -1;
+                const int ii = ex ? i + (axis == 0 ? d : 0) : i, jj = ex ? j + (axis == 1 ? d : 0) : j,
+                          kk = ex ? k + (axis == 2 ? d : 0) : k;
+                xv += omega * xc[(ii >> (g.cx - 1)) + (long long)cnx * ((jj >> (g.cy - 1)) + (long long)cny * (kk >> (g.cz - 1)))];
+            }
+            double p = aa[s] * xv;
+            tt[s] = ex ? p : 0.0;
+        }
+#pragma unroll
+        for (int s = 1; s < NS; s++) acc -= tt[s];
+    }
+    x[c] = aa[0] != 0.0 ? acc / aa[0] : 0.0;
 }
 
 // bc[C] = sum over the aggregate of (b - A x)  (residual + restriction fused).  The aggregate is walked as a
@@ -573,31 +619,38 @@ __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, co
 // flight instead of eight rows' one after the other (measured: 13 us -> latency of one row on the small levels);
 // lane 0 of the group then adds the eight residuals in the fixed order q = 0..7 of restrict_cell.
 template <int NS>
-__global__ void __launch_bounds__(256) restrict_kernel(const double* __restrict__ a, const double* __restrict__ b,
-                                                       const double* __restrict__ x, LevGeom f, LevGeom cg,
+__global__ void __launch_bounds__(256) restrict_kernel(const double* __restrict__ a, const double* b,
+                                                       const double* x, LevGeom f, LevGeom cg,
                                                        double* __restrict__ bc) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long C = t >> 3;
     const int q = (int)(t & 7);
-    double r = 0.0;
+    bool ok = false;
+    int i = 0, j = 0, k = 0;
     if (C < cg.n) {
         int I, Jc, Kc;
         tpb_ijk(C, cg.nx, cg.ny, I, Jc, Kc);
         const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
-        const int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
-        const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + k) & 1) == 0;
-        if (ok) {
-            long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
-            double acc = b[c] - a[c] * x[c];
+        i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
+        ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + k) & 1) == 0;
+    }
+    pdl_launch_dependents();
+    const long long c = ok ? i + (long long)f.nx * (j + (long long)f.ny * k) : 0;
+    double aa[NS];
 #pragma unroll
-            for (int s = 1; s < NS; s++) {
-                bool ex;
-                long long nb = nbr_clamped(f.nx, f.ny, f.nz, i, j, k, c, s, ex);
-                double p = a[(long long)s * f.n + c] * x[nb];
-                acc -= ex ? p : 0.0;
-            }
-            r = acc;
+    for (int s = 0; s < NS; s++) aa[s] = ok ? a[(long long)s * f.n + c] : 0.0;   // the operator does not change during a solve
+    pdl_wait();
+    double r = 0.0;
+    if (ok) {
+        double acc = b[c] - aa[0] * x[c];
+#pragma unroll
+        for (int s = 1; s < NS; s++) {
+            bool ex;
+            long long nb = nbr_clamped(f.nx, f.ny, f.nz, i, j, k, c, s, ex);
+            double p = aa[s] * x[nb];
+            acc -= ex ? p : 0.0;
         }
+        r = acc;
     }
     // whole warps reach this point (the grid is padded to full blocks)
     const int base = (threadIdx.x & 31) & ~7;
@@ -964,6 +1017,23 @@ __global__ void __launch_bounds__(256) bjacobi_kernel(const double* __restrict__
 // =================================================================================================
 inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// launch with programmatic stream serialisation (see pdl_wait); TPB_PDL=0 launches normally
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    static const bool on = !(getenv("TPB_PDL") && atoi(getenv("TPB_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = on ? 1 : 0;
+    TPB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 inline LevGeom lg(const MgLevel& L) { return LevGeom{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.n}; }
 
 void mg_free_levels(MgHier& m) {
@@ -1157,12 +1227,11 @@ void mg_rbgs(tpb_handle_s* h, const MgLevel& L, bool zero_guess, const MgLevel* 
     long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
     for (int col = 0; col < 2; col++) {
         if (coarse && col == 0)
-            rbgs_kernel<NS, true><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col, 0, coarse->x, coarse->nx,
-                                                                             coarse->ny, omega);
+            launch_pdl(rbgs_kernel<NS, true>, nblk(threads, 256), 256, h->stream, L.a, L.b, L.x, g, col, 0, coarse->x,
+                       coarse->nx, coarse->ny, omega);
         else
-            rbgs_kernel<NS, false><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col,
-                                                                              (zero_guess && col == 0) ? 1 : 0, nullptr, 0, 0,
-                                                                              0.0);
+            launch_pdl(rbgs_kernel<NS, false>, nblk(threads, 256), 256, h->stream, L.a, L.b, L.x, g, col,
+                       (zero_guess && col == 0) ? 1 : 0, nullptr, 0, 0, 0.0);
         h->launches++;
     }
 }
@@ -1201,7 +1270,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         }
         for (int s = 0; s < pre; s++) mg_rbgs<NS>(h, L, s == 0);
         MgLevel& Cc = m.lev[l + 1];
-        restrict_kernel<NS><<<nblk(Cc.n * 8, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
+        launch_pdl(restrict_kernel<NS>, nblk(Cc.n * 8, 256), 256, h->stream, L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
         h->launches++;
     }
     if (!dist) {
