@@ -1,5 +1,6 @@
 // tpb_api.cu - extern "C" surface of libtpb200.so (declared in include/tpb200.h).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -20,6 +21,11 @@ const double* tpb_pc_weights_impl(tpb_handle_s* h, int f);
 long long tpb_pc_rbgs_pass_impl(tpb_handle_s* h, int col);
 
 static thread_local std::string g_err;
+
+bool tpb_pdl_enabled() {
+    static const bool on = !(getenv("TPB_PDL") && atoi(getenv("TPB_PDL")) == 0);
+    return on;
+}
 
 #define TPB_TRY(h)  \
     try {           \

@@ -23,6 +23,8 @@ template <int K>
 __global__ void __launch_bounds__(RB) mdot_kernel(size_t n, const double* __restrict__ x, const double* __restrict__ Y,
                                                   size_t ldy, int kact, double* __restrict__ partial,
                                                   unsigned int* __restrict__ counter, double* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     double acc[K];
 #pragma unroll
     for (int j = 0; j < K; j++) acc[j] = 0.0;
@@ -72,6 +74,8 @@ struct Coef {
 template <int K>
 __global__ void __launch_bounds__(256) maxpy_kernel(size_t n, double* __restrict__ y, const double* __restrict__ V,
                                                     size_t ldv, int kact, Coef cf, double scale) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
         double a = y[i];
 #pragma unroll
@@ -82,15 +86,21 @@ __global__ void __launch_bounds__(256) maxpy_kernel(size_t n, double* __restrict
 }
 
 __global__ void axpby_kernel(size_t n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
 }
 __global__ void waxpy_kernel(size_t n, double a, const double* __restrict__ x, const double* __restrict__ y,
                              double* __restrict__ w) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         w[i] = fma(a, x[i], y[i]);
 }
 __global__ void scale_kernel(size_t n, double a, double* __restrict__ x) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         x[i] *= a;
 }
@@ -164,15 +174,15 @@ void ensure_red(tpb_handle_s* h) {
 
 void tpb_axpy(tpb_handle_s* h, size_t n, double a, const double* x, double* y) { tpb_axpby(h, n, a, x, 1.0, y); }
 void tpb_axpby(tpb_handle_s* h, size_t n, double a, const double* x, double b, double* y) {
-    axpby_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(n, a, x, b, y);
+    launch_pdl(axpby_kernel, grid_for(n, 256), 256, h->stream, n, a, x, b, y);
     h->launches++;
 }
 void tpb_waxpy(tpb_handle_s* h, size_t n, double a, const double* x, const double* y, double* w) {
-    waxpy_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(n, a, x, y, w);
+    launch_pdl(waxpy_kernel, grid_for(n, 256), 256, h->stream, n, a, x, y, w);
     h->launches++;
 }
 void tpb_scale(tpb_handle_s* h, size_t n, double a, double* x) {
-    scale_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(n, a, x);
+    launch_pdl(scale_kernel, grid_for(n, 256), 256, h->stream, n, a, x);
     h->launches++;
 }
 void tpb_copy(tpb_handle_s* h, size_t n, const double* x, double* y) {
@@ -187,8 +197,8 @@ void tpb_mdot_dev(tpb_handle_s* h, size_t n, const double* x, const double* Y, s
     unsigned blocks = grid_for(n, RB);
     for (int j0 = 0; j0 < k; j0 += KC) {
         int kact = k - j0 < KC ? k - j0 : KC;
-        mdot_kernel<KC><<<blocks, RB, 0, h->stream>>>(n, x, Y + (size_t)j0 * ldy, ldy, kact, h->red_partial,
-                                                      h->red_counter, h->red_out + out_off + j0);
+        launch_pdl(mdot_kernel<KC>, blocks, RB, h->stream, n, x, Y + (size_t)j0 * ldy, ldy, kact, h->red_partial,
+                   h->red_counter, h->red_out + out_off + j0);
         h->launches++;
     }
 }
@@ -219,7 +229,7 @@ void tpb_maxpy(tpb_handle_s* h, size_t n, double* y, const double* V, size_t ldv
         int kact = k - j0 < KC ? k - j0 : KC;
         Coef cf;
         for (int j = 0; j < KC; j++) cf.c[j] = j < kact ? c[j0 + j] : 0.0;
-        maxpy_kernel<KC><<<grid_for(n, 256), 256, 0, h->stream>>>(n, y, V + (size_t)j0 * ldv, ldv, kact, cf, 1.0);
+        launch_pdl(maxpy_kernel<KC>, grid_for(n, 256), 256, h->stream, n, y, V + (size_t)j0 * ldv, ldv, kact, cf, 1.0);
         h->launches++;
     }
 }
@@ -230,7 +240,7 @@ void tpb_maxpy_scale(tpb_handle_s* h, size_t n, double* y, const double* V, size
     TPB_REQUIRE(k <= KC, TPB_ERR_ARG, "maxpy_scale: group too large");
     Coef cf;
     for (int j = 0; j < KC; j++) cf.c[j] = j < k ? c[j] : 0.0;
-    maxpy_kernel<KC><<<grid_for(n, 256), 256, 0, h->stream>>>(n, y, V, ldv, k, cf, scale);
+    launch_pdl(maxpy_kernel<KC>, grid_for(n, 256), 256, h->stream, n, y, V, ldv, k, cf, scale);
     h->launches++;
 }
 

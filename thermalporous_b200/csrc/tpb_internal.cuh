@@ -73,6 +73,36 @@ __device__ __forceinline__ void tpb_ijk(long long c, int nx, int ny, int& i, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): the ~190 small kernels of one PC application depend on each other in a
+// chain, and most of a small level's pass is launch latency plus two dependent rounds of loads.  Kernels launched
+// through launch_pdl() may start while their predecessor drains: they decode their cell and load what does not
+// change during a solve (their row of the operator, decoupling weights) first, and only then wait for the
+// predecessor's results (pdl_wait), so one round of loads and the launch overlap the previous kernel.  Rules:
+// every thread of a kernel launched this way executes pdl_wait before it exits (a kernel that finished without
+// waiting would let ITS successor overtake the predecessor), and nothing a predecessor writes is touched before it.
+// pdl_launch_dependents at the top of a kernel lets the successor start as soon as all blocks are resident.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// launch with programmatic stream serialisation; TPB_PDL=0 launches normally
+bool tpb_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = tpb_pdl_enabled() ? 1 : 0;
+    TPB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward-mode dual numbers (value + N partials); everything is unrolled into registers
 // ---------------------------------------------------------------------------------------------
 template <int N>

@@ -520,15 +520,6 @@ __device__ __forceinline__ void rbgs_cell(const double* __restrict__ a, const do
     x[c] = d0 != 0.0 ? acc / d0 : 0.0;
 }
 
-// Programmatic dependent launch (sm_90+): the ~190 small kernels of one PC application depend on each other in a
-// chain, and most of a small level's pass is launch latency plus two dependent rounds of loads.  Kernels launched
-// through launch_pdl() may start while their predecessor drains: they decode their cell and load their row of the
-// operator (constant during a solve) first, and only then wait for the predecessor's results (pdl_wait), so one of
-// the two load rounds and the launch overlap the previous pass.  Every thread executes pdl_wait before it exits -
-// a kernel that finished without waiting would let ITS successor overtake the predecessor.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 template <int NS, bool PROLONG>
 __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a, const double* b,
                                                    double* x, LevGeom g, int col, int zero_guess,
@@ -781,6 +772,8 @@ __device__ __forceinline__ void cyc_up(const TailArgs& A, int l1, int l0, long l
 
 template <int NS>
 __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
+    pdl_launch_dependents();
+    pdl_wait();
     BlockBarrier bar;
     const long long tid = threadIdx.x, nth = blockDim.x;
     cyc_down<NS>(A, 0, A.nlev - 1, tid, nth, bar);
@@ -791,11 +784,15 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs A) {
 // multi-rank hierarchies: the single-CTA zone above the gather level is cut in two around the all-gather
 template <int NS>
 __global__ void __launch_bounds__(TAIL_THREADS) tail_down_kernel(TailArgs A) {
+    pdl_launch_dependents();
+    pdl_wait();
     BlockBarrier bar;
     cyc_down<NS>(A, 0, A.nlev - 1, (long long)threadIdx.x, (long long)blockDim.x, bar);
 }
 template <int NS>
 __global__ void __launch_bounds__(TAIL_THREADS) tail_up_kernel(TailArgs A) {
+    pdl_launch_dependents();
+    pdl_wait();
     BlockBarrier bar;
     cyc_up<NS>(A, A.nlev - 1, 0, (long long)threadIdx.x, (long long)blockDim.x, bar);
 }
@@ -807,9 +804,13 @@ __global__ void __launch_bounds__(256) cpr_restrict_kernel(const double* __restr
                                                            const double* __restrict__ w2, long long n,
                                                            double* __restrict__ rp) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    double v = x[c] - w1[c] * x[n + c];
-    if (NF == 3) v -= w2[c] * x[2 * n + c];
+    pdl_launch_dependents();
+    const bool in = c < n;
+    const double a1 = in ? w1[c] : 0.0, a2 = (in && NF == 3) ? w2[c] : 0.0;   // set-up data: before the wait
+    pdl_wait();
+    if (!in) return;
+    double v = x[c] - a1 * x[n + c];
+    if (NF == 3) v -= a2 * x[2 * n + c];
     rp[c] = v;
 }
 // CPTR restriction: r_a = x_a - w_a x_S, a in (p, T)
@@ -818,25 +819,35 @@ __global__ void __launch_bounds__(256) cptr_restrict_kernel(const double* __rest
                                                             const double* __restrict__ w1, long long n,
                                                             double* __restrict__ rp, double* __restrict__ rT) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
+    pdl_launch_dependents();
+    const bool in = c < n;
+    const double a0 = in ? w0[c] : 0.0, a1 = in ? w1[c] : 0.0;   // set-up data: before the wait
+    pdl_wait();
+    if (!in) return;
     double xs = NF == 3 ? x[2 * n + c] : 0.0;
-    rp[c] = x[c] - w0[c] * xs;
-    rT[c] = x[n + c] - w1[c] * xs;
+    rp[c] = x[c] - a0 * xs;
+    rT[c] = x[n + c] - a1 * xs;
 }
 // r -= A00[.,a,b] x  (one coupling block of the 2x2 primary system)
 template <int DIM>
 __global__ void __launch_bounds__(256) a00_sub_kernel(const double* __restrict__ A00, int a, int b,
-                                                      const double* __restrict__ x, Geom g, double* __restrict__ r) {
+                                                      const double* x, Geom g, double* r) {
     const long long n = g.n;
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    int i, j, k;
-    tpb_ijk(c, g.nx, g.ny, i, j, k);
+    pdl_launch_dependents();
+    const bool in = c < n;
+    int i = 0, j = 0, k = 0;
+    double co[2 * DIM + 1];
+    if (in) tpb_ijk(c, g.nx, g.ny, i, j, k);
+#pragma unroll
+    for (int s = 0; s < 2 * DIM + 1; s++) co[s] = in ? A00[((long long)(s * 2 + a) * 2 + b) * n + c] : 0.0;
+    pdl_wait();
+    if (!in) return;
     double acc = 0.0;
 #pragma unroll
     for (int s = 0; s < 2 * DIM + 1; s++) {
         long long nb = nbr_cell(g.nx, g.ny, g.nz, i, j, k, c, s);
-        if (nb >= 0) acc += A00[((long long)(s * 2 + a) * 2 + b) * n + c] * x[nb];
+        if (nb >= 0) acc += co[s] * x[nb];
     }
     r[c] -= acc;
 }
@@ -952,11 +963,20 @@ __global__ void __launch_bounds__(128) ilu_half_kernel(const float* __restrict__
     const int nxh = (nx + 1) >> 1;
     const long long nth = (long long)ny * nz * nxh;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nth) return;
-    int ih, j, k;
-    tpb_ijk(t, nxh, ny, ih, j, k);
-    int i = 2 * ih + ((col + j + k) & 1);
-    if (i >= nx) return;
+    pdl_launch_dependents();
+    bool active = t < nth;
+    int ih = 0, j = 0, k = 0, i = 0;
+    if (active) {
+        tpb_ijk(t, nxh, ny, ih, j, k);
+        i = 2 * ih + ((col + j + k) & 1);
+        active = i < nx;
+    }
+    // the inverted diagonal block is set-up data: load it before waiting for the predecessor
+    float dd[NF * NF];
+#pragma unroll
+    for (int e = 0; e < NF * NF; e++) dd[e] = active ? Dc[((long long)col * NF * NF + e) * nth + t] : 0.f;
+    pdl_wait();
+    if (!active) return;
     long long c = i + (long long)nx * (j + (long long)ny * k);
     double tt[NF];
 #pragma unroll
@@ -982,12 +1002,11 @@ __global__ void __launch_bounds__(128) ilu_half_kernel(const float* __restrict__
     double v[NF];
 #pragma unroll
     for (int a = 0; a < NF; a++) v[a] = mode == 2 ? tt[a] : r[(long long)a * n + c] - tt[a];
-    const float* Dp = Dc + ((long long)col * NF * NF) * nth + t;
 #pragma unroll
     for (int a = 0; a < NF; a++) {
         double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < NF; q++) acc += (double)Dp[(long long)(a * NF + q) * nth] * v[q];
+        for (int q = 0; q < NF; q++) acc += (double)dd[a * NF + q] * v[q];
         if (mode == 2)
             z[(long long)a * n + c] -= acc;
         else
@@ -1016,23 +1035,6 @@ __global__ void __launch_bounds__(256) bjacobi_kernel(const double* __restrict__
 // host side
 // =================================================================================================
 inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
-
-// launch with programmatic stream serialisation (see pdl_wait); TPB_PDL=0 launches normally
-template <typename... KArgs, typename... Args>
-void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
-    static const bool on = !(getenv("TPB_PDL") && atoi(getenv("TPB_PDL")) == 0);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(block, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = on ? 1 : 0;
-    TPB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
-}
 
 inline LevGeom lg(const MgLevel& L) { return LevGeom{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.n}; }
 
@@ -1275,12 +1277,12 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     }
     if (!dist) {
         if (ltail < m.nlev) {
-            tail_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(tail_args(ltail));
+            launch_pdl(tail_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));
             h->launches++;
         }
     } else {
         if (ltail < last) {
-            tail_down_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(tail_args(ltail));
+            launch_pdl(tail_down_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));
             h->launches++;
         }
         MgHier* mp = &m;
@@ -1289,7 +1291,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         });
         mg_vcycle_t<NS>(h, *m.glob);
         if (ltail < last) {
-            tail_up_kernel<NS><<<1, TAIL_THREADS, 0, h->stream>>>(tail_args(ltail));
+            launch_pdl(tail_up_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));
             h->launches++;
         }
     }
@@ -1426,7 +1428,7 @@ void stage2_apply_t(tpb_handle_s* h, const double* r, double* z) {
     long long threads = (long long)h->g.ny * h->g.nz * ((h->g.nx + 1) >> 1);
     const int seq[3][2] = {{0, 0}, {1, 1}, {0, 2}};
     for (int q = 0; q < 3; q++) {
-        ilu_half_kernel<NF, DIM><<<nblk(threads, 128), 128, 0, h->stream>>>(pc->Lc, pc->Dc, r, z, h->g, seq[q][0], seq[q][1]);
+        launch_pdl(ilu_half_kernel<NF, DIM>, nblk(threads, 128), 128, h->stream, pc->Lc, pc->Dc, r, z, h->g, seq[q][0], seq[q][1]);
         h->launches++;
     }
 }
@@ -1439,14 +1441,14 @@ void stage1_apply_t(tpb_handle_s* h, const double* x, double* y) {
     double* rp = pc->t2;
     if (o.stage1 == TPB_S1_CPR) {
         tpb_zero(h, (size_t)(NF - 1) * n, y + n);
-        cpr_restrict_kernel<NF><<<nblk(n, 256), 256, 0, h->stream>>>(x, pc->w[1], pc->w[2], n, rp);
+        launch_pdl(cpr_restrict_kernel<NF>, nblk(n, 256), 256, h->stream, x, pc->w[1], pc->w[2], n, rp);
         h->launches++;
         mg_apply(h, pc->mg_p, rp, y);
         return;
     }
     double* rT = pc->t2 + n;
     if (NF == 3) tpb_zero(h, (size_t)n, y + 2 * n);
-    cptr_restrict_kernel<NF><<<nblk(n, 256), 256, 0, h->stream>>>(x, pc->w[0], pc->w[1], n, rp, rT);
+    launch_pdl(cptr_restrict_kernel<NF>, nblk(n, 256), 256, h->stream, x, pc->w[0], pc->w[1], n, rp, rT);
     h->launches++;
     double* yp = y;
     double* yT = y + n;
@@ -1455,10 +1457,10 @@ void stage1_apply_t(tpb_handle_s* h, const double* x, double* y) {
         mg_apply(h, pc->mg_T, rT, yT);
         return;
     }
-    a00_sub_kernel<DIM><<<nblk(n, 256), 256, 0, h->stream>>>(pc->A00, 1, 0, yp, h->g, rT);
+    launch_pdl(a00_sub_kernel<DIM>, nblk(n, 256), 256, h->stream, pc->A00, 1, 0, yp, h->g, rT);
     h->launches++;
     mg_apply(h, pc->mg_T, rT, yT);
-    a00_sub_kernel<DIM><<<nblk(n, 256), 256, 0, h->stream>>>(pc->A00, 0, 1, yT, h->g, rp);
+    launch_pdl(a00_sub_kernel<DIM>, nblk(n, 256), 256, h->stream, pc->A00, 0, 1, yT, h->g, rp);
     h->launches++;
     mg_apply(h, pc->mg_p, rp, yp);
 }

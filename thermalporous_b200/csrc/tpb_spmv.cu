@@ -16,10 +16,12 @@ __global__ void __launch_bounds__(256) spmv_kernel(const double* __restrict__ J,
                                                    double* __restrict__ y, Geom g) {
     const long long n = g.n;
     long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n) return;
+    pdl_launch_dependents();
     const int nx = g.nx, ny = g.ny, np = g.np;
-    int i, j, k;
-    tpb_ijk(cell, nx, ny, i, j, k);
+    int i = 0, j = 0, k = 0;
+    if (cell < n) tpb_ijk(cell, nx, ny, i, j, k);
+    pdl_wait();   // x (and its ghost planes) come from the predecessor
+    if (cell >= n) return;
 
     double acc[NF];
 #pragma unroll
@@ -73,7 +75,7 @@ void launch_t(tpb_handle_s* h, const double* J, const double* x, double* y) {
     const long long n = h->g.n;
     const int threads = 256;
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
-    spmv_kernel<NF, DIM><<<blocks, threads, 0, h->stream>>>(J, x, h->x_lo, h->x_hi, y, h->g);
+    launch_pdl(spmv_kernel<NF, DIM>, blocks, (unsigned)threads, h->stream, J, x, (const double*)h->x_lo, (const double*)h->x_hi, y, h->g);
     h->launches++;
     TPB_CUDA(cudaGetLastError());
 }
