@@ -6,6 +6,8 @@
 // and a sum of k doubles.  NCCL is resolved at run time with dlopen("libnccl.so.2") - the copy
 // torch already mapped into the process - so the single-GPU library has no NCCL link dependency.
 #include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "tpb_internal.cuh"
 
@@ -76,6 +78,74 @@ __global__ void pack_planes_kernel(const double* __restrict__ x, long long n, in
     last[t] = x[(long long)f * n + n - np + q];
 }
 
+// ---- peer-memory kernels ---------------------------------------------------------------------------
+// sum of `count` doubles over the ranks, in rank order (identical bits on every rank); one CTA
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PView v, double* buf, int count) {
+    __shared__ unsigned long long ep;
+    if (threadIdx.x == 0) ep = ++v.epoch[P2P_SLOT_AR];
+    __syncthreads();
+    const unsigned long long e = ep;
+    const int par = (int)(e & 1);
+    for (int r = 0; r < v.nranks; r++) {
+        double* dst = p2p_ar_area(v, r, par, v.rank);
+        for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = buf[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < v.nranks) {
+        p2p_store_flag(p2p_flag(v, threadIdx.x, P2P_SLOT_AR, v.rank), e);
+        p2p_wait(v, P2P_SLOT_AR, threadIdx.x, e);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < v.nranks; r++) sum += __ldcg(p2p_ar_area(v, v.rank, par, r) + i);
+        buf[i] = sum;
+    }
+}
+
+// boundary planes of x straight into the neighbours' mailboxes; the last block to finish publishes the epoch
+__global__ void __launch_bounds__(256) halo_push_kernel(P2PView v, const double* __restrict__ x, long long n, int np,
+                                                        int nfields, int has_lo, int has_hi, unsigned int* ticket) {
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&v.epoch[P2P_SLOT_HALO_LO]) + 1;
+    const int par = (int)(e & 1);
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)np * nfields) {
+        const int f = (int)(t / np), q = (int)(t % np);
+        // my first plane is the upper ghost of the rank below; my last plane the lower ghost of the rank above
+        if (has_lo) p2p_halo_area(v, v.rank - 1, false, par)[t] = x[(long long)f * n + q];
+        if (has_hi) p2p_halo_area(v, v.rank + 1, true, par)[t] = x[(long long)f * n + n - np + q];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(&v.epoch[P2P_SLOT_HALO_LO]) = e;
+        if (has_lo) p2p_store_flag(p2p_flag(v, v.rank - 1, P2P_SLOT_HALO_HI, v.rank), e);
+        if (has_hi) p2p_store_flag(p2p_flag(v, v.rank + 1, P2P_SLOT_HALO_LO, v.rank), e);
+    }
+}
+
+// wait for the neighbours' planes of the current epoch and copy them out of the mailbox
+__global__ void __launch_bounds__(256) halo_pull_kernel(P2PView v, int np, int nfields, int has_lo, int has_hi,
+                                                        double* __restrict__ lo, double* __restrict__ hi) {
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(&v.epoch[P2P_SLOT_HALO_LO]);
+    const int par = (int)(e & 1);
+    if (threadIdx.x == 0) {
+        if (has_lo) p2p_wait(v, P2P_SLOT_HALO_LO, v.rank - 1, e);
+        if (has_hi) p2p_wait(v, P2P_SLOT_HALO_HI, v.rank + 1, e);
+    }
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)np * nfields) {
+        if (has_lo) lo[t] = __ldcg(p2p_halo_area(v, v.rank, true, par) + t);
+        if (has_hi) hi[t] = __ldcg(p2p_halo_area(v, v.rank, false, par) + t);
+    }
+}
+
 }  // namespace
 
 struct CommState {
@@ -86,6 +156,15 @@ struct CommState {
     size_t cap = 0;
     std::vector<int> planes;       // owned planes of every rank along the slab axis (filled on first use)
     double* scratch = nullptr;     // nranks doubles
+    // peer-memory mailboxes (tpb_internal.cuh)
+    bool p2p_ok = false;
+    int p2p_mask = 0;              // TPB_P2P bits: 1 all-reduce, 2 halo, 4 multigrid gather
+    char* my_box = nullptr;
+    std::vector<char*> peer_box;   // opened IPC mappings (nullptr for this rank)
+    unsigned long long* epoch = nullptr;
+    int* err = nullptr;
+    unsigned int* ticket = nullptr;
+    P2PView view{};
 };
 
 void tpb_comm_free(tpb_handle_s* h) {
@@ -94,6 +173,12 @@ void tpb_comm_free(tpb_handle_s* h) {
     tpb_dfree(h->comm->send_first);
     tpb_dfree(h->comm->send_last);
     tpb_dfree(h->comm->scratch);
+    for (char* q : h->comm->peer_box)
+        if (q) cudaIpcCloseMemHandle(q);
+    tpb_dfree(h->comm->my_box);
+    tpb_dfree(h->comm->epoch);
+    tpb_dfree(h->comm->err);
+    tpb_dfree(h->comm->ticket);
     delete h->comm;
     h->comm = nullptr;
 }
@@ -106,6 +191,13 @@ void tpb_halo_vector(tpb_handle_s* h, const double* x, int nfields, double* lo, 
     CommState* c = h->comm;
     const int np = h->g.np;
     size_t cnt = (size_t)np * nfields;
+    if (c->p2p_ok && (c->p2p_mask & 2) && (long long)cnt <= c->view.halo_cap) {
+        const unsigned blocks = (unsigned)((cnt + 255) / 256);
+        halo_push_kernel<<<blocks, 256, 0, h->stream>>>(c->view, x, h->g.n, np, nfields, h->g.has_lo, h->g.has_hi, c->ticket);
+        halo_pull_kernel<<<blocks, 256, 0, h->stream>>>(c->view, np, nfields, h->g.has_lo, h->g.has_hi, lo, hi);
+        h->launches += 2;
+        return;
+    }
     if (cnt > c->cap) {
         tpb_dfree(c->send_first);
         tpb_dfree(c->send_last);
@@ -132,6 +224,109 @@ void tpb_halo_vector(tpb_handle_s* h, const double* x, int nfields, double* lo, 
 void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count) {
     if (!h->comm || h->comm->nranks == 1) return;
     TPB_NCCL(api().AllReduce(dev_buf, dev_buf, (size_t)count, ncclFloat64, ncclSum, h->comm->comm, h->stream));
+}
+
+// the Krylov / Newton reductions: peer-memory all-reduce when the mailboxes are up, NCCL otherwise
+void tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count) {
+    if (!h->comm || h->comm->nranks == 1) return;
+    CommState* c = h->comm;
+    if (c->p2p_ok && (c->p2p_mask & 1) && count <= P2P_AR_MAX) {
+        p2p_allreduce_kernel<<<1, 256, 0, h->stream>>>(c->view, dev_buf, count);
+        h->launches++;
+        return;
+    }
+    tpb_allreduce_sum(h, dev_buf, count);
+}
+
+bool tpb_p2p_view(tpb_handle_s* h, int want, P2PView* v) {
+    if (!h->comm || !h->comm->p2p_ok || !(h->comm->p2p_mask & want)) return false;
+    *v = h->comm->view;
+    return true;
+}
+
+void tpb_p2p_check(tpb_handle_s* h) {
+    if (!h->comm || !h->comm->p2p_ok) return;
+    int e = 0;
+    TPB_CUDA(cudaMemcpyAsync(&e, h->comm->err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    TPB_REQUIRE(e == 0, TPB_ERR_NCCL, "a peer-memory exchange timed out (a rank stopped or left the common call sequence)");
+}
+
+// Set up the mailboxes: allocate, exchange the CUDA IPC handles over NCCL, map the peers' boxes.  Any failure (IPC
+// not permitted in this container, no peer access) leaves the NCCL paths in charge.  TPB_P2P=0 disables, default 7.
+static void p2p_init(tpb_handle_s* h) {
+    CommState* c = h->comm;
+    const int mask = getenv("TPB_P2P") ? atoi(getenv("TPB_P2P")) : 7;
+    if (mask == 0 || c->nranks < 2 || c->nranks > P2P_MAXR) return;
+    NcclApi& a = api();
+    P2PView& v = c->view;
+    memset(&v, 0, sizeof(v));
+    v.rank = c->rank;
+    v.nranks = c->nranks;
+    v.halo_cap = (long long)h->g.np * TPB_MAXF;
+    v.mg_cap = 8192;
+    long long off = 4096;   // flags: P2P_NSLOT * P2P_MAXR words
+    v.off_ar = off;
+    off += 2LL * P2P_MAXR * P2P_AR_MAX * 8;
+    v.off_halo_lo = off;
+    off += 2 * v.halo_cap * 8;
+    v.off_halo_hi = off;
+    off += 2 * v.halo_cap * 8;
+    v.off_mg = off;
+    off += 4 * v.mg_cap * 8;
+    const size_t bytes = (size_t)off;
+    bool fine = cudaMalloc(&c->my_box, bytes) == cudaSuccess && cudaMemset(c->my_box, 0, bytes) == cudaSuccess;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    fine = fine && cudaIpcGetMemHandle(&mine, c->my_box) == cudaSuccess;
+    if (!fine) cudaGetLastError();
+    // every rank takes part in the exchange whatever happened locally: [ok flag | 64-byte handle] as 9 doubles
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    const int W = 9;
+    std::vector<double> all((size_t)W * c->nranks, 0.0), me(W, 0.0);
+    me[0] = fine ? 1.0 : 0.0;
+    memcpy(&me[1], &mine, 64);
+    double* dev = tpb_dalloc<double>((size_t)W * c->nranks);
+    TPB_CUDA(cudaMemcpyAsync(dev + (size_t)W * c->rank, me.data(), W * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TPB_NCCL(a.AllGather(dev + (size_t)W * c->rank, dev, (size_t)W, ncclFloat64, c->comm, h->stream));
+    TPB_CUDA(cudaMemcpyAsync(all.data(), dev, all.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    c->peer_box.assign(c->nranks, nullptr);
+    for (int r = 0; r < c->nranks; r++) fine = fine && all[(size_t)W * r] == 1.0;
+    for (int r = 0; r < c->nranks && fine; r++) {
+        if (r == c->rank) {
+            v.box[r] = c->my_box;
+            continue;
+        }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, &all[(size_t)W * r + 1], 64);
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            fine = false;
+            break;
+        }
+        c->peer_box[r] = (char*)q;
+        v.box[r] = (char*)q;
+    }
+    // agree on the outcome: everybody or nobody
+    me[0] = fine ? 0.0 : 1.0;
+    TPB_CUDA(cudaMemcpyAsync(dev, me.data(), sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TPB_NCCL(a.AllReduce(dev, dev, 1, ncclFloat64, ncclSum, c->comm, h->stream));
+    TPB_CUDA(cudaMemcpyAsync(me.data(), dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    tpb_dfree(dev);
+    if (me[0] != 0.0) return;   // some rank could not map a peer: NCCL paths stay in charge
+    c->epoch = tpb_dalloc<unsigned long long>(P2P_NSLOT);
+    c->err = tpb_dalloc<int>(1);
+    c->ticket = tpb_dalloc<unsigned int>(1);
+    TPB_CUDA(cudaMemset(c->epoch, 0, P2P_NSLOT * sizeof(unsigned long long)));
+    TPB_CUDA(cudaMemset(c->err, 0, sizeof(int)));
+    TPB_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+    v.epoch = c->epoch;
+    v.err = c->err;
+    c->p2p_mask = mask;
+    c->p2p_ok = true;
 }
 
 void tpb_allreduce_max(tpb_handle_s* h, double* dev_buf, int count) {
@@ -192,6 +387,7 @@ void tpb_comm_init_impl(tpb_handle_s* h, const void* id128, int rank, int nranks
     ncclUniqueId id;
     memcpy(id.internal, id128, 128);
     TPB_NCCL(api().CommInitRank(&h->comm->comm, nranks, id, rank));
+    p2p_init(h);
 }
 
 void tpb_comm_unique_id_impl(void* out128) {

@@ -103,6 +103,63 @@ inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Peer-memory mailboxes (tpb_comm.cu): every rank owns one cudaMalloc'ed mailbox, mapped into every other rank's
+// process with CUDA IPC, so a kernel can store straight into a peer's HBM over NVLink/NVSwitch.  A message is
+// data stores + fence.sys + a release store of the slot's epoch number into the receiver's flag word; the receiver
+// spins on its own (local) flag with acquire loads and reads the data with L1-bypassing loads.  Data areas are
+// double-buffered on the epoch's parity: a sender can only be one message ahead of a receiver, because message
+// e+1 of any slot is sent after the sender has consumed the receiver's message e.  Spins are bounded; a time-out
+// raises the error word, which the host turns into TPB_ERR_NCCL at the next synchronisation.
+// ---------------------------------------------------------------------------------------------
+constexpr int P2P_MAXR = 16;        // ranks
+constexpr int P2P_AR_MAX = 256;     // doubles per all-reduce
+enum { P2P_SLOT_AR = 0, P2P_SLOT_HALO_LO = 1, P2P_SLOT_HALO_HI = 2, P2P_SLOT_MG = 3 /* + hierarchy (0|1) */, P2P_NSLOT = 8 };
+constexpr long long P2P_SPIN_MAX = 4000000;   // ~ seconds
+
+struct P2PView {
+    char* box[P2P_MAXR];            // box[r]: rank r's mailbox as mapped in this process
+    unsigned long long* epoch;      // this rank's per-slot message counters (device)
+    int* err;                       // time-out word (device)
+    int rank, nranks;
+    long long off_ar, off_halo_lo, off_halo_hi, off_mg;   // byte offsets of the data areas inside a mailbox
+    long long halo_cap, mg_cap;     // doubles per parity buffer
+};
+
+__device__ __forceinline__ unsigned long long* p2p_flag(const P2PView& v, int r, int slot, int src) {
+    return reinterpret_cast<unsigned long long*>(v.box[r]) + slot * P2P_MAXR + src;
+}
+__device__ __forceinline__ void p2p_store_flag(unsigned long long* f, unsigned long long e) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e) : "memory");
+}
+__device__ __forceinline__ unsigned long long p2p_load_flag(const unsigned long long* f) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    return v;
+}
+// wait until rank `src` has delivered message `e` of `slot` into THIS rank's mailbox
+__device__ __forceinline__ bool p2p_wait(const P2PView& v, int slot, int src, unsigned long long e) {
+    const unsigned long long* f = p2p_flag(v, v.rank, slot, src);
+    for (long long spin = 0; spin < P2P_SPIN_MAX; spin++) {
+        if (p2p_load_flag(f) >= e) return true;
+        __nanosleep(64);
+    }
+    atomicExch(v.err, 1);
+    return false;
+}
+__device__ __forceinline__ double* p2p_ar_area(const P2PView& v, int r, int par, int src) {
+    return reinterpret_cast<double*>(v.box[r] + v.off_ar) + ((long long)par * P2P_MAXR + src) * P2P_AR_MAX;
+}
+__device__ __forceinline__ double* p2p_halo_area(const P2PView& v, int r, bool from_lo, int par) {
+    return reinterpret_cast<double*>(v.box[r] + (from_lo ? v.off_halo_lo : v.off_halo_hi)) + (long long)par * v.halo_cap;
+}
+__device__ __forceinline__ double* p2p_mg_area(const P2PView& v, int r, int hier, int par) {
+    return reinterpret_cast<double*>(v.box[r] + v.off_mg) + ((long long)hier * 2 + par) * v.mg_cap;
+}
+// true (and *v filled) when the handle has working mailboxes; `want` = bit of TPB_P2P (1 all-reduce, 2 halo, 4 multigrid)
+bool tpb_p2p_view(tpb_handle_s* h, int want, P2PView* v);
+void tpb_p2p_check(tpb_handle_s* h);   // throws if a peer-memory wait timed out
+
+// ---------------------------------------------------------------------------------------------
 // forward-mode dual numbers (value + N partials); everything is unrolled into registers
 // ---------------------------------------------------------------------------------------------
 template <int N>
@@ -338,6 +395,7 @@ void tpb_launch_assemble(tpb_handle_s* h, const double* u, const double* u_old, 
 void tpb_launch_spmv(tpb_handle_s* h, const double* J, const double* x, double* y);
 void tpb_halo_vector(tpb_handle_s* h, const double* x, int nfields, double* lo, double* hi);
 void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count);
+void tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count);
 int tpb_comm_rank(tpb_handle_s* h);
 int tpb_comm_size(tpb_handle_s* h);
 const std::vector<int>& tpb_comm_planes(tpb_handle_s* h);

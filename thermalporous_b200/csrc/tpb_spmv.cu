@@ -84,7 +84,13 @@ void launch_t(tpb_handle_s* h, const double* J, const double* x, double* y) {
 
 // x must already have its ghost planes in h->x_lo / h->x_hi when the slab has neighbours
 void tpb_launch_spmv(tpb_handle_s* h, const double* J, const double* x, double* y) {
-    if (h->g.has_lo || h->g.has_hi) tpb_comm_op(h, [h, x]() { tpb_halo_vector(h, x, h->nf, h->x_lo, h->x_hi); });
+    if (h->g.has_lo || h->g.has_hi) {
+        P2PView pv;
+        if (tpb_p2p_view(h, 2, &pv))
+            tpb_halo_vector(h, x, h->nf, h->x_lo, h->x_hi);   // peer-memory push/pull kernels: fine inside a graph capture
+        else
+            tpb_comm_op(h, [h, x]() { tpb_halo_vector(h, x, h->nf, h->x_lo, h->x_hi); });
+    }
     if (h->nf == 2) {
         if (h->g.dim == 2)
             launch_t<2, 2>(h, J, x, y);
