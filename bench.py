@@ -115,11 +115,22 @@ class ClockSampler:
 
 
 class NpOps:
+    """time-loop helpers on HOST fields; with a process group the bounds are reduced over the ranks' slabs"""
+
+    def __init__(self, dist=None, device=None):
+        self.dist, self.device = dist, device
+
     def copy(self, d, s):
         d[...] = s
 
     def minmax(self, u, f):
-        return float(u[f].min()), float(u[f].max())
+        lo, hi = float(u[f].min()), float(u[f].max())
+        if self.dist is not None:
+            import torch
+            t = torch.tensor([-lo, hi], device=self.device, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            lo, hi = -float(t[0].item()), float(t[1].item())
+        return lo, hi
 
     def clip(self, u, f, lo, hi):
         np.clip(u[f], lo, hi, out=u[f])
@@ -271,21 +282,26 @@ def run_b200(args):
     value = n_glob * res.total_nits / (ms * 1e-3) / 1e6
 
     # ---- timed region 2 (e2e): HOST buffers through tpb_newton_solve_host, same steps from the same state
-    e2e = None
-    if world == 1:
+    # (every rank copies its own slab in and out; the byte counts are the whole job's)
+    if True:
         hu = torch.empty_like(snap_u, device="cpu").pin_memory()
         huo = torch.empty_like(snap_u, device="cpu").pin_memory()
         hu.copy_(snap_u)
         huo.copy_(snap_uo)
         hu_np, huo_np = hu.numpy(), huo.numpy()
-        res2, ms2, wall2, _, _ = timed(lambda a, b, dt: eng.newton_solve_host(a, b, dt), hu_np, huo_np, NpOps())
+        res2, ms2, wall2, _, _ = timed(lambda a, b, dt: eng.newton_solve_host(a, b, dt), hu_np, huo_np,
+                                         NpOps(dist if world > 1 else None, eng.device))
         nbytes = hu_np.nbytes
         e2e = {"value": n_glob * res2.total_nits / (ms2 * 1e-3) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": 2 * nbytes * world, "d2h_bytes_per_step": nbytes * world, "ms_per_step": ms2 / args.steps,
                "nits": res2.nits_vec, "api": "tpb_newton_solve_host (host u, u_old in; host u out)"}
         # same physics from the same state: the two regions must agree on the converged fields
         dev_final = u.cpu().numpy()
         diff = max(float(np.abs(dev_final[f] - hu_np[f]).max() / np.abs(dev_final[f]).max()) for f in range(3))
+        if world > 1:
+            t = torch.tensor([diff], device=eng.device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            diff = float(t.item())
         e2e["max_rel_diff_vs_resident_run"] = diff
 
     # ---- rooflines, each kernel timed alone with CUDA events on the handle's stream (burst peak applies)
@@ -313,7 +329,10 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(geo.Nz, refine, args.scale), "cells": n_glob, "cells_per_gpu": n_loc,
                        "solver": desc, "l2": "working set per Newton step (Jacobian 565 MB + Krylov basis) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": "z-slab x%d" % world},
+                       "parallelism": "z-slab x%d" % world,
+                       "exchanges": ("single slab" if world == 1 else
+                                     "peer-memory mailboxes over NVLink (mask %d: 1 Krylov all-reduce, 2 halo planes, 4 multigrid "
+                                     "gather); NCCL for the rest" % eng.peer_mode() if eng.peer_mode() else "NCCL")},
             "nits": res.nits_vec, "lits": res.lits_vec, "dt_days": [d / 86400.0 for d in res.dt_vec],
             "failed_solves": res.failed_solves, "failed": res.failed, "host_wall_ms_per_step": wall * 1e3 / args.steps,
             "phase_ms": {"assemble": sum(s.t_assemble_ms for s in res.stats), "pc_setup": sum(s.t_pcsetup_ms for s in res.stats),

@@ -2,7 +2,8 @@
 Runs tests/mgpu_check.py under torchrun: assembly, SpMV and a Newton solve over 2 slabs must reproduce
 the single-domain CPU restatement (F, J, J x to 1e-12; converged fields to 1e-8).  Two gather thresholds of the
 multi-rank multigrid: the default (this small grid is gathered whole, so the hierarchy is the single-domain one
-and the Krylov counts match the CPU run) and 300 cells (slab-local levels above an all-gathered coarse level)."""
+and the Krylov counts match the CPU run) and 300 cells (slab-local levels above an all-gathered coarse level); each with the exchanges through the
+peer-memory mailboxes (csrc/tpb_comm.cu) and through NCCL."""
 import os
 import subprocess
 import sys
@@ -13,8 +14,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("p2p", ["7", "0"])   # peer-memory mailboxes (halo, all-reduce, gather) | NCCL only
 @pytest.mark.parametrize("gather", [None, "300"])
-def test_two_slabs_reproduce_single_domain(gather):
+def test_two_slabs_reproduce_single_domain(gather, p2p):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -22,6 +24,7 @@ def test_two_slabs_reproduce_single_domain(gather):
     env.pop("TPB_MG_GATHER", None)
     if gather:
         env["TPB_MG_GATHER"] = gather
+    env["TPB_P2P"] = p2p
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29531", os.path.join(ROOT, "tests", "mgpu_check.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)

@@ -58,7 +58,7 @@ SYMBOLS = [
     "tpb_set_sources", "tpb_assemble", "tpb_set_state_ghost", "tpb_jacobian_size", "tpb_nstencil", "tpb_spmv",
     "tpb_solver_defaults", "tpb_set_solver_opts", "tpb_pc_setup", "tpb_pc_apply", "tpb_ksp_solve",
     "tpb_newton_solve", "tpb_newton_solve_host", "tpb_field_minmax", "tpb_clip_field", "tpb_dot",
-    "tpb_comm_init", "tpb_comm_unique_id", "tpb_exchange_static", "tpb_launch_count", "tpb_time_kernel",
+    "tpb_comm_init", "tpb_comm_unique_id", "tpb_exchange_static", "tpb_comm_peer_mode", "tpb_launch_count", "tpb_time_kernel",
     "tpb_stream", "tpb_sync", "tpb_pc_mg_nlevels", "tpb_pc_mg_level", "tpb_pc_mg_apply", "tpb_pc_stage2_apply",
     "tpb_pc_get_weights",
 ]
@@ -108,6 +108,7 @@ def load():
     lib.tpb_comm_init.argtypes = [vp, vp, i, i]
     lib.tpb_comm_unique_id.argtypes = [vp]
     lib.tpb_exchange_static.argtypes = [vp]
+    lib.tpb_comm_peer_mode.argtypes = [vp]
     lib.tpb_launch_count.argtypes = [vp]
     lib.tpb_launch_count.restype = C.c_int64
     lib.tpb_time_kernel.argtypes = [vp, i, dp, dp, d, dp, dp, dp, dp, i, C.POINTER(d)]

@@ -487,6 +487,7 @@ int tpb_pc_get_weights(tpb_handle h, int f, double* out) {
 }
 
 int64_t tpb_launch_count(tpb_handle h) { return h ? h->launches : 0; }
+int tpb_comm_peer_mode(tpb_handle h) { return h ? tpb_comm_peer_mode_impl(h) : 0; }
 void* tpb_stream(tpb_handle h) { return h ? (void*)h->stream : nullptr; }
 int tpb_sync(tpb_handle h) {
     TPB_TRY(h)

@@ -44,12 +44,20 @@ constexpr int NSCR1 = 3, NSCR2 = 7;
 
 template <int NF>
 __global__ void __launch_bounds__(256) props_kernel(Fields<NF> fl, long long n, int np, int has_lo, int has_hi,
-                                                    DevParams P, double* __restrict__ scr) {
+                                                    DevParams P, double* __restrict__ scr, int late_wait) {
+    // PDL chain of an assembly (launch_t): [sources_kernel ->] props_kernel -> assemble_kernel on one stream.
+    // late_wait: the predecessor is sources_kernel, which this kernel does not depend on - it only has to finish
+    // before assemble_kernel reads its output, so the wait moves to the end (every thread still waits before it
+    // exits, tpb_internal.cuh) and the two run side by side.  Otherwise the predecessor may have produced u.
+    pdl_launch_dependents();
+    if (!late_wait) pdl_wait();
     const long long ne = n + 2LL * np;
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ne) return;
     long long c = e - np;
-    if ((c < 0 && !has_lo) || (c >= n && !has_hi)) return;
+    if (e >= ne || (c < 0 && !has_lo) || (c >= n && !has_hi)) {
+        if (late_wait) pdl_wait();
+        return;
+    }
     double p = gl(fl.u[0], c, n, np), T = gl(fl.u[1], c, n, np);
     double ro, ro_p, ro_T, imo, imo_T;
     oil_rho_d(P, p, T, ro, ro_p, ro_T);
@@ -66,6 +74,7 @@ __global__ void __launch_bounds__(256) props_kernel(Fields<NF> fl, long long n, 
         scr[5 * ne + e] = rw * imw;
         scr[6 * ne + e] = rw_T * imw + rw * imw_T;
     }
+    if (late_wait) pdl_wait();
 }
 
 // static face transmissibilities area * harmonic K of the face between a cell and its +axis neighbour
@@ -238,14 +247,24 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
                                                              double* __restrict__ J) {
     const long long n = g.n;
     long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n) return;
+    // scr comes from props_kernel and src_acc from sources_kernel, the two predecessors (PDL chain, see
+    // props_kernel); u, u_old and the static fields were complete before either started
+    if (cell >= n) {
+        pdl_wait();
+        return;
+    }
     const int nx = g.nx, ny = g.ny, np = g.np;
     const long long ne = n + 2LL * np;
     int i, j, k;
     tpb_ijk(cell, nx, ny, i, j, k);
+    const double phi = fl.phi.v[cell];
+    const double po = u_old[cell], To = u_old[n + cell];
+    const double So_old = NF == 3 ? u_old[2 * n + cell] : 1.0;
+    const double ro_old = oil_rho_v(P, po, To);
+    const double rw_old = NF == 3 ? water_rho_v(po, To) : 0.0;
+    pdl_wait();
 
     const Side<NF> me = load_side<NF, false>(P, fl, scr, n, np, ne, cell);
-    const double phi = fl.phi.v[cell];
 
     double R[NF];
     double D[NF][NF];
@@ -253,9 +272,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
     // ---- accumulation (cell integrals) ------------------------------------------------------
     {
         constexpr double CO_P = 5.5e-4, CO_T = -2.5e-4, CW_P = 3.98854e-4;
-        const double po = u_old[cell], To = u_old[n + cell];
         const double w = g.vol * idt;
-        const double ro_old = oil_rho_v(P, po, To);
         const double rk = w * (1.0 - phi) * P.rho_r * P.c_r;
         const double wp = w * phi;
         if (NF == 2) {
@@ -268,8 +285,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
                 D[1][1] = wp * P.c_v_o * (CO_T * me.ro * me.T + me.ro) + rk;
             }
         } else {
-            const double So = u_old[2 * n + cell];
-            const double rw_old = water_rho_v(po, To);
+            const double So = So_old;
             const double S = me.S, Sw = 1.0 - me.S, T = me.T;
             const double aw = wp * (me.rw * Sw - rw_old * (1.0 - So));                  // twophase.py:333
             const double ao = wp * (me.ro * S - ro_old * So);                           // :337
@@ -436,6 +452,7 @@ __global__ void sources_kernel(int ncells, const int64_t* __restrict__ cells, co
                                const tpb_source* __restrict__ ent, const double* __restrict__ u,
                                const double* __restrict__ Kx, const double* __restrict__ Ky, long long n, DevParams P,
                                double* __restrict__ acc_out) {
+    pdl_launch_dependents();   // props_kernel may run beside this kernel (it waits for it at its end)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncells) return;
     long long cell = cells[t];
@@ -542,7 +559,7 @@ void launch_k(tpb_handle_s* h, const Fields<NF>& fl, const double* u_old, double
     const unsigned blocks = (unsigned)((n + threads - 1) / threads);
     static int variant = getenv("TPB_ASM_MINB") ? atoi(getenv("TPB_ASM_MINB")) : 4;
 #define TPB_ASM(JAC, MINB) \
-    assemble_kernel<NF, DIM, JAC, HALO, MINB><<<blocks, threads, 0, h->stream>>>(fl, u_old, h->scr, tr, h->nsrc_cells > 0 ? h->src_index : nullptr, h->src_acc, 1.0 / dt, h->g, h->dp, F, J)
+    launch_pdl(assemble_kernel<NF, DIM, JAC, HALO, MINB>, blocks, threads, h->stream, fl, u_old, (const double*)h->scr, tr, (const int*)(h->nsrc_cells > 0 ? h->src_index : nullptr), (const double*)h->src_acc, 1.0 / dt, h->g, h->dp, F, J)
     if (J) {
         if (variant == 3)
             TPB_ASM(true, 3);
@@ -591,24 +608,23 @@ void launch_t(tpb_handle_s* h, const double* u, const double* u_old, double dt, 
         h->launches++;
         h->trans_dirty = false;
     }
+    // One stream, three kernels chained by programmatic dependent launch: the few source cells (a normal launch:
+    // everything before it is complete when it starts), the property pre-pass running beside them, then the
+    // flux kernel, whose blocks start while the pre-pass drains and wait for both before they read the scratch.
+    const bool pdl = tpb_pdl_enabled();
     if (h->nsrc_cells > 0) {
-        // fork: the few source cells are evaluated on the side stream while the property pre-pass runs
-        TPB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
-        TPB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
         const unsigned sb = (unsigned)((h->nsrc_cells + 127) / 128);
         if (J)
-            sources_kernel<NF, true><<<sb, 128, 0, h->stream2>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
-                                                                h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, h->src_acc);
+            sources_kernel<NF, true><<<sb, 128, 0, h->stream>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
+                                                               h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, h->src_acc);
         else
-            sources_kernel<NF, false><<<sb, 128, 0, h->stream2>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
-                                                                 h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, h->src_acc);
+            sources_kernel<NF, false><<<sb, 128, 0, h->stream>>>(h->nsrc_cells, h->src_cell, h->src_off, h->src_ent, u,
+                                                                h->fld[TPB_KX], h->fld[TPB_KY], n, h->dp, h->src_acc);
         h->launches++;
-        TPB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
     }
-    props_kernel<NF><<<(unsigned)((ne + 255) / 256), 256, 0, h->stream>>>(fl, n, np, h->g.has_lo, h->g.has_hi, h->dp,
-                                                                         h->scr);
+    launch_pdl(props_kernel<NF>, (unsigned)((ne + 255) / 256), 256, h->stream, fl, n, np, h->g.has_lo, h->g.has_hi, h->dp,
+               h->scr, (pdl && h->nsrc_cells > 0) ? 1 : 0);
     h->launches++;
-    if (h->nsrc_cells > 0) TPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     if (h->g.has_lo || h->g.has_hi)
         launch_k<NF, DIM, true>(h, fl, u_old, dt, F, J);
     else

@@ -146,6 +146,32 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(P2PView v, int np, int n
     }
 }
 
+// all-gather of the multigrid gather level's right-hand side: this rank's section goes into every rank's mailbox,
+// then the whole level is copied out of the local mailbox once every section of the epoch has arrived; one CTA
+__global__ void __launch_bounds__(1024) mg_gather_kernel(P2PView v, int hier, double* buf, long long my_off,
+                                                         long long my_cnt, long long total) {
+    __shared__ unsigned long long ep;
+    if (threadIdx.x == 0) ep = ++v.epoch[P2P_SLOT_MG + hier];
+    __syncthreads();
+    const unsigned long long e = ep;
+    const int par = (int)(e & 1);
+    for (int r = 0; r < v.nranks; r++) {
+        if (r == v.rank) continue;
+        double* dst = p2p_mg_area(v, r, hier, par) + my_off;
+        for (long long i = threadIdx.x; i < my_cnt; i += blockDim.x) dst[i] = buf[my_off + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < v.nranks && threadIdx.x != v.rank) {
+        p2p_store_flag(p2p_flag(v, threadIdx.x, P2P_SLOT_MG + hier, v.rank), e);
+        p2p_wait(v, P2P_SLOT_MG + hier, threadIdx.x, e);
+    }
+    __syncthreads();
+    const double* src = p2p_mg_area(v, v.rank, hier, par);
+    for (long long i = threadIdx.x; i < total; i += blockDim.x)
+        if (i < my_off || i >= my_off + my_cnt) buf[i] = __ldcg(src + i);
+}
+
 }  // namespace
 
 struct CommState {
@@ -236,6 +262,17 @@ void tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count) {
         return;
     }
     tpb_allreduce_sum(h, dev_buf, count);
+}
+
+// in-place all-gather of one small vector through the mailboxes (the multigrid gather level, once per V-cycle);
+// false when the mailboxes are not available or the level does not fit - the caller then goes through NCCL
+bool tpb_p2p_gather(tpb_handle_s* h, int hier, double* buf, long long my_off, long long my_cnt, long long total) {
+    if (!h->comm || !h->comm->p2p_ok || !(h->comm->p2p_mask & 4)) return false;
+    CommState* c = h->comm;
+    if (total > c->view.mg_cap || hier < 0 || hier > 1) return false;
+    mg_gather_kernel<<<1, 1024, 0, h->stream>>>(c->view, hier, buf, my_off, my_cnt, total);
+    h->launches++;
+    return true;
 }
 
 bool tpb_p2p_view(tpb_handle_s* h, int want, P2PView* v) {
@@ -374,6 +411,7 @@ void tpb_allgatherv(tpb_handle_s* h, double* buf, const long long* off, const lo
     TPB_NCCL(a.GroupEnd());
 }
 
+int tpb_comm_peer_mode_impl(tpb_handle_s* h) { return (h->comm && h->comm->p2p_ok) ? h->comm->p2p_mask : 0; }
 int tpb_comm_rank(tpb_handle_s* h) { return h->comm ? h->comm->rank : 0; }
 int tpb_comm_size(tpb_handle_s* h) { return h->comm ? h->comm->nranks : 1; }
 

@@ -157,7 +157,9 @@ __device__ __forceinline__ double* p2p_mg_area(const P2PView& v, int r, int hier
 }
 // true (and *v filled) when the handle has working mailboxes; `want` = bit of TPB_P2P (1 all-reduce, 2 halo, 4 multigrid)
 bool tpb_p2p_view(tpb_handle_s* h, int want, P2PView* v);
-void tpb_p2p_check(tpb_handle_s* h);   // throws if a peer-memory wait timed out
+bool tpb_p2p_gather(tpb_handle_s* h, int hier, double* buf, long long my_off, long long my_cnt, long long total);
+void tpb_p2p_check(tpb_handle_s* h);
+int tpb_comm_peer_mode_impl(tpb_handle_s* h);   // throws if a peer-memory wait timed out
 
 // ---------------------------------------------------------------------------------------------
 // forward-mode dual numbers (value + N partials); everything is unrolled into registers

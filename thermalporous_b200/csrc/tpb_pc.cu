@@ -1286,9 +1286,13 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
             h->launches++;
         }
         MgHier* mp = &m;
-        tpb_comm_op(h, [h, mp]() {
-            tpb_allgatherv(h, mp->glob->lev[0].b, mp->goff.data(), mp->gcnt.data(), 1, 0);
-        });
+        const int rank = tpb_comm_rank(h);
+        const long long gn = m.goff.back() + m.gcnt.back();
+        // peer-memory gather kernel (stays inside the graph capture), else NCCL between two graphs
+        if (!tpb_p2p_gather(h, &m == &h->pc->mg_T ? 1 : 0, m.glob->lev[0].b, m.goff[rank], m.gcnt[rank], gn))
+            tpb_comm_op(h, [h, mp]() {
+                tpb_allgatherv(h, mp->glob->lev[0].b, mp->goff.data(), mp->gcnt.data(), 1, 0);
+            });
         mg_vcycle_t<NS>(h, *m.glob);
         if (ltail < last) {
             launch_pdl(tail_up_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));

@@ -222,6 +222,7 @@ void tpb_ksp_solve_impl(tpb_handle_s* h, const double* J, const double* b, doubl
         }
     }
     TPB_CUDA(cudaStreamSynchronize(h->stream));
+    tpb_p2p_check(h);   // a timed-out peer-memory wait anywhere in this solve is an error, not a result
     *its_out = its;
     *reason_out = reason;
     *rnorm_out = rnorm;

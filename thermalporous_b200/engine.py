@@ -239,5 +239,9 @@ class Engine:
         self._chk(self.lib.tpb_comm_unique_id(buf))
         return buf.raw
 
+    def peer_mode(self) -> int:
+        """bit mask of the exchanges that go through peer memory instead of NCCL (tpb_comm_peer_mode)"""
+        return int(self.lib.tpb_comm_peer_mode(self.h))
+
     def exchange_static(self):
         self._chk(self.lib.tpb_exchange_static(self.h))

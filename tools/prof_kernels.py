@@ -21,11 +21,19 @@ gen = torch.Generator(device="cuda").manual_seed(1234)
 rnd = lambda lo, hi: torch.rand(n, generator=gen, device="cuda", dtype=torch.float64) * (hi - lo) + lo
 u = torch.stack([prm.p_ref + rnd(-0.05, 0.05), rnd(288.7, 300.0), rnd(0.85, 0.95)])
 uo = torch.stack([prm.p_ref + rnd(-0.05, 0.05), rnd(288.7, 300.0), rnd(0.85, 0.95)])
+mode = sys.argv[1] if len(sys.argv) > 1 else "all"
 for _ in range(2):
     F, J = eng.assemble(u, uo, 864.0)
 eng.pc_setup(J, u, 864.0)
 x = torch.randn(3, n, generator=gen, device="cuda", dtype=torch.float64)
-for _ in range(2):
-    y = eng.pc_apply(x)
-    z = eng.spmv(J, y)
-print("ok", float(z.abs().max()))
+if mode in ("all", "spmv"):
+    for _ in range(2):
+        z = eng.spmv(J, x)
+if mode in ("all", "pc"):
+    # component by component, so that a short `--launch-count` reaches every kernel family: ILU(0) half sweeps,
+    # one pressure V-cycle (smoother passes of every level, restrictions, the single-CTA tail), one multi-dot
+    r = eng.stage2_apply(x)
+    v = eng.mg_apply(0, x[0].contiguous())
+    eng.set_solver_opts(ksp_max_it=4)
+    d = eng.ksp_solve(J, x)   # four Arnoldi steps: multi-dot / multi-axpy
+print("ok", mode)
