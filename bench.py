@@ -332,7 +332,7 @@ def run_b200(args):
                        "parallelism": "z-slab x%d" % world,
                        "exchanges": ("single slab" if world == 1 else
                                      "peer-memory mailboxes over NVLink (mask %d: 1 Krylov all-reduce, 2 halo planes, 4 multigrid "
-                                     "gather); NCCL for the rest" % eng.peer_mode() if eng.peer_mode() else "NCCL")},
+                                     "gather, 8 halo fused into the SpMV kernel); NCCL for the rest" % eng.peer_mode() if eng.peer_mode() else "NCCL")},
             "nits": res.nits_vec, "lits": res.lits_vec, "dt_days": [d / 86400.0 for d in res.dt_vec],
             "failed_solves": res.failed_solves, "failed": res.failed, "host_wall_ms_per_step": wall * 1e3 / args.steps,
             "phase_ms": {"assemble": sum(s.t_assemble_ms for s in res.stats), "pc_setup": sum(s.t_pcsetup_ms for s in res.stats),

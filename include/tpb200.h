@@ -184,7 +184,8 @@ int tpb_comm_init(tpb_handle h, const void* nccl_unique_id, int rank, int nranks
 int tpb_comm_unique_id(void* out128);
 int tpb_exchange_static(tpb_handle h);   /* ghost planes of phi,K*,kT after tpb_set_field */
 /* Which exchanges go through the peer-memory mailboxes (CUDA IPC over NVLink) instead of NCCL: bit 0 Krylov
-   all-reduce, bit 1 halo planes, bit 2 multigrid gather level; 0 = NCCL only (single rank, IPC not available,
+   all-reduce, bit 1 halo planes, bit 2 multigrid gather level, bit 3 halo exchange fused into the SpMV kernel (one
+   launch pushes the boundary planes, multiplies, and reads the neighbours' planes); 0 = NCCL only (single rank, IPC not available,
    or TPB_P2P=0 in the environment). */
 int tpb_comm_peer_mode(tpb_handle h);
 

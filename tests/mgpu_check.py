@@ -58,7 +58,7 @@ ok = eF < 1e-12 and eJ < 1e-12 and ey < 1e-12 and st.reason > 0 and eu < 1e-8 an
 # the multi-rank multigrid must stay as good a preconditioner as the single-domain one (block ILU per slab aside)
 ok = ok and st.lits <= sc.lits + (3 if not os.environ.get("TPB_MG_GATHER") else 12)
 # the exchanges must have gone the way the environment asked for (TPB_P2P unset = mailboxes)
-want_peer = int(os.environ.get("TPB_P2P", "7"))
+want_peer = int(os.environ.get("TPB_P2P", "15"))
 ok = ok and eng.peer_mode() == want_peer
 print("rank %d/%d: peer mode %d (asked %d) F %.1e J %.1e spmv %.1e | newton nits %d (cpu %d) lits %d (cpu %d) reason %d fields %.1e | %s"
       % (rank, world, eng.peer_mode(), want_peer, eF, eJ, ey, st.nits, sc.nits, st.lits, sc.lits, st.reason, eu, "OK" if ok else "FAIL"), flush=True)

@@ -14,8 +14,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("p2p", ["7", "0"])   # peer-memory mailboxes (halo, all-reduce, gather) | NCCL only
-@pytest.mark.parametrize("gather", [None, "300"])
+# TPB_P2P: 15 = every exchange through the peer-memory mailboxes with the halo fused into the SpMV kernel,
+# 7 = mailboxes with separate push/pull kernels, 0 = NCCL only
+@pytest.mark.parametrize("gather,p2p", [(None, "15"), ("300", "15"), (None, "7"), ("300", "0")])
 def test_two_slabs_reproduce_single_domain(gather, p2p):
     import torch
     if torch.cuda.device_count() < 2:

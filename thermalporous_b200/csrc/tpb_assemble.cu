@@ -238,41 +238,77 @@ struct Trans {
     const double* lo;
 };
 
-template <int NF, int DIM, bool JAC, bool HALO, int MINB>
-__global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, const double* __restrict__ u_old,
-                                                             const double* __restrict__ scr, Trans tr,
-                                                             const int* __restrict__ src_index,
-                                                             const double* __restrict__ src_acc, double idt, Geom g,
-                                                             DevParams P, double* __restrict__ F,
-                                                             double* __restrict__ J) {
+// what a cell's row needs from global memory besides the Sides: face transmissibilities, old state, source slot
+template <int NF, int DIM>
+struct CellIn {
+    double aK[2 * DIM + 1];   // area * K_facet per stencil slot (0 where the face does not exist)
+    bool ex[2 * DIM + 1];
+    double uo[NF];
+    int si;
+};
+
+template <int NF, int DIM>
+__device__ __forceinline__ CellIn<NF, DIM> load_cell_in(const Geom& g, const Trans& tr, const double* __restrict__ u_old,
+                                                        const int* __restrict__ src_index, long long cell, int i, int j,
+                                                        int k) {
+    CellIn<NF, DIM> in;
     const long long n = g.n;
-    long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // scr comes from props_kernel and src_acc from sources_kernel, the two predecessors (PDL chain, see
-    // props_kernel); u, u_old and the static fields were complete before either started
-    if (cell >= n) {
-        pdl_wait();
-        return;
-    }
     const int nx = g.nx, ny = g.ny, np = g.np;
-    const long long ne = n + 2LL * np;
-    int i, j, k;
-    tpb_ijk(cell, nx, ny, i, j, k);
-    const double phi = fl.phi.v[cell];
-    const double po = u_old[cell], To = u_old[n + cell];
-    const double So_old = NF == 3 ? u_old[2 * n + cell] : 1.0;
-    const double ro_old = oil_rho_v(P, po, To);
-    const double rw_old = NF == 3 ? water_rho_v(po, To) : 0.0;
-    pdl_wait();
+    in.aK[0] = 0.0;
+    in.ex[0] = true;
+#pragma unroll
+    for (int s = 1; s < 2 * DIM + 1; s++) {
+        const int axis = (s - 1) >> 1;
+        const bool hi_side = ((s - 1) & 1) != 0;   // neighbour has the higher index => this cell is '+'
+        bool exists;
+        long long nb;
+        double aK;                                 // area * K_facet
+        if (axis == 0) {
+            exists = hi_side ? (i < nx - 1) : (i > 0);
+            nb = cell + (hi_side ? 1 : -1);
+            aK = exists ? tr.t[0][hi_side ? cell : nb] : 0.0;
+        } else if (axis == 1) {
+            if (DIM == 2) {
+                exists = hi_side ? (j < ny - 1 || g.has_hi) : (j > 0 || g.has_lo);
+                nb = cell + (hi_side ? nx : -nx);
+                aK = !exists ? 0.0 : (hi_side ? tr.t[1][cell] : (nb >= 0 ? tr.t[1][nb] : tr.lo[cell]));
+            } else {
+                exists = hi_side ? (j < ny - 1) : (j > 0);
+                nb = cell + (hi_side ? nx : -nx);
+                aK = exists ? tr.t[1][hi_side ? cell : nb] : 0.0;
+            }
+        } else {
+            exists = hi_side ? (k < g.nz - 1 || g.has_hi) : (k > 0 || g.has_lo);
+            nb = cell + (hi_side ? (long long)np : -(long long)np);
+            aK = !exists ? 0.0 : (hi_side ? tr.t[2][cell] : (nb >= 0 ? tr.t[2][nb] : tr.lo[cell]));
+        }
+        in.aK[s] = aK;
+        in.ex[s] = exists;
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) in.uo[f] = u_old[(long long)f * n + cell];
+    in.si = src_index ? src_index[cell] : -1;
+    return in;
+}
 
-    const Side<NF> me = load_side<NF, false>(P, fl, scr, n, np, ne, cell);
-
+// One cell's row: accumulation, the 2*DIM facet integrals seen from the row side, source cells, stores.  `nbr(s, nb)`
+// returns the Side of the neighbour through stencil slot s (cell index nb).
+template <int NF, int DIM, bool JAC, class NbrF>
+__device__ __forceinline__ void assemble_cell(const DevParams& P, const Geom& g, const CellIn<NF, DIM>& in,
+                                              const double* __restrict__ src_acc, double idt, long long cell,
+                                              const Side<NF>& me, double phi, NbrF&& nbr, double* __restrict__ F,
+                                              double* __restrict__ J) {
+    const long long n = g.n;
+    const int nx = g.nx, np = g.np;
     double R[NF];
     double D[NF][NF];
 
     // ---- accumulation (cell integrals) ------------------------------------------------------
     {
         constexpr double CO_P = 5.5e-4, CO_T = -2.5e-4, CW_P = 3.98854e-4;
+        const double po = in.uo[0], To = in.uo[1];
         const double w = g.vol * idt;
+        const double ro_old = oil_rho_v(P, po, To);
         const double rk = w * (1.0 - phi) * P.rho_r * P.c_r;
         const double wp = w * phi;
         if (NF == 2) {
@@ -285,7 +321,8 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
                 D[1][1] = wp * P.c_v_o * (CO_T * me.ro * me.T + me.ro) + rk;
             }
         } else {
-            const double So = So_old;
+            const double So = in.uo[NF - 1];
+            const double rw_old = water_rho_v(po, To);
             const double S = me.S, Sw = 1.0 - me.S, T = me.T;
             const double aw = wp * (me.rw * Sw - rw_old * (1.0 - So));                  // twophase.py:333
             const double ao = wp * (me.ro * S - ro_old * So);                           // :337
@@ -316,28 +353,11 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
     for (int s = 1; s < 2 * DIM + 1; s++) {
         const int axis = (s - 1) >> 1;
         const bool hi_side = ((s - 1) & 1) != 0;   // neighbour has the higher index => this cell is '+'
-        bool exists;
-        long long nb;
-        double aK;                                 // area * K_facet
-        if (axis == 0) {
-            exists = hi_side ? (i < nx - 1) : (i > 0);
-            nb = cell + (hi_side ? 1 : -1);
-            aK = exists ? tr.t[0][hi_side ? cell : nb] : 0.0;
-        } else if (axis == 1) {
-            if (DIM == 2) {
-                exists = hi_side ? (j < ny - 1 || g.has_hi) : (j > 0 || g.has_lo);
-                nb = cell + (hi_side ? nx : -nx);
-                aK = !exists ? 0.0 : (hi_side ? tr.t[1][cell] : (nb >= 0 ? tr.t[1][nb] : tr.lo[cell]));
-            } else {
-                exists = hi_side ? (j < ny - 1) : (j > 0);
-                nb = cell + (hi_side ? nx : -nx);
-                aK = exists ? tr.t[1][hi_side ? cell : nb] : 0.0;
-            }
-        } else {
-            exists = hi_side ? (k < g.nz - 1 || g.has_hi) : (k > 0 || g.has_lo);
-            nb = cell + (hi_side ? (long long)np : -(long long)np);
-            aK = !exists ? 0.0 : (hi_side ? tr.t[2][cell] : (nb >= 0 ? tr.t[2][nb] : tr.lo[cell]));
-        }
+        const bool exists = in.ex[s];
+        const double aK = in.aK[s];
+        const long long nb = cell + (axis == 0 ? (hi_side ? 1 : -1)
+                                               : (axis == DIM - 1 ? (hi_side ? (long long)np : -(long long)np)
+                                                                  : (hi_side ? (long long)nx : -(long long)nx)));
         double O[NF][NF];
 #pragma unroll
         for (int r = 0; r < NF; r++)
@@ -345,9 +365,7 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
             for (int c = 0; c < NF; c++) O[r][c] = 0.0;
 
         if (exists) {
-            const bool slab_axis = (axis == DIM - 1);
-            const Side<NF> ot = (HALO && slab_axis) ? load_side<NF, true>(P, fl, scr, n, np, ne, nb)
-                                                    : load_side<NF, false>(P, fl, scr, n, np, ne, nb);
+            const Side<NF> ot = nbr(s, nb);
             const double gh = (axis == 2) ? 0.5 * P.g : 0.0;
             const double ih = g.ih[axis], Ak = g.area[axis] * ih;
             double f[NF], dP[NF][NF], dM[NF][NF];
@@ -391,8 +409,8 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
         }
     }
 
-    if (src_index) {   // wells / heaters in this cell (sources_kernel)
-        const int si = src_index[cell];
+    {   // wells / heaters in this cell (sources_kernel)
+        const int si = in.si;
         if (si >= 0) {
             const double* o = src_acc + (long long)si * (NF + NF * NF);
 #pragma unroll
@@ -417,6 +435,39 @@ __global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, cons
                 jp += n;
             }
     }
+}
+
+// K1/K2: thread per cell, neighbour values straight from global memory (L1/L2 serve the re-reads).  A plane-marching
+// variant with cp.async-staged shared-memory tiles (32x8 .. 64x2 threads, three rotating plane buffers, own column's
+// lower plane in registers) produced the same bits and was measured 1.4-2.2x SLOWER on B200 at 60x220x85 (0.224-0.349
+// ms against 0.156 ms): the per-plane block barrier puts a block's warps in lock-step and the staging costs 15
+// cp.async per cell, more than the L1/L2 re-reads it saves.  It was removed; DESIGN.md section 4 keeps the numbers.
+template <int NF, int DIM, bool JAC, bool HALO, int MINB>
+__global__ void __launch_bounds__(128, MINB) assemble_kernel(Fields<NF> fl, const double* __restrict__ u_old,
+                                                             const double* __restrict__ scr, Trans tr,
+                                                             const int* __restrict__ src_index,
+                                                             const double* __restrict__ src_acc, double idt, Geom g,
+                                                             DevParams P, double* __restrict__ F,
+                                                             double* __restrict__ J) {
+    const long long n = g.n;
+    long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // scr comes from props_kernel and src_acc from sources_kernel, the two predecessors (PDL chain, see
+    // props_kernel); u, u_old and the static fields were complete before either started
+    pdl_wait();
+    if (cell >= n) return;
+    const int nx = g.nx, ny = g.ny, np = g.np;
+    const long long ne = n + 2LL * np;
+    int i, j, k;
+    tpb_ijk(cell, nx, ny, i, j, k);
+    const Side<NF> me = load_side<NF, false>(P, fl, scr, n, np, ne, cell);
+    const double phi = fl.phi.v[cell];
+    auto nbr = [&](int s, long long nb) {
+        const bool slab_axis = ((s - 1) >> 1) == DIM - 1;
+        return (HALO && slab_axis) ? load_side<NF, true>(P, fl, scr, n, np, ne, nb)
+                                   : load_side<NF, false>(P, fl, scr, n, np, ne, nb);
+    };
+    const CellIn<NF, DIM> in = load_cell_in<NF, DIM>(g, tr, u_old, src_index, cell, i, j, k);
+    assemble_cell<NF, DIM, JAC>(P, g, in, src_acc, idt, cell, me, phi, nbr, F, J);
 }
 
 // ---- well / heater source terms ---------------------------------------------------------------

@@ -206,8 +206,8 @@ void tpb_mdot_dev(tpb_handle_s* h, size_t n, const double* x, const double* Y, s
 // sum the first `count` queued results over the ranks, copy them to the host and synchronise
 void tpb_red_get(tpb_handle_s* h, int count, double* host_out) {
     ensure_red(h);
-    tpb_allreduce_sum_hot(h, h->red_out, count);
-    TPB_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (!tpb_allreduce_sum_hot(h, h->red_out, count, h->red_host))
+        TPB_CUDA(cudaMemcpyAsync(h->red_host, h->red_out, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     TPB_CUDA(cudaStreamSynchronize(h->stream));
     for (int j = 0; j < count; j++) host_out[j] = h->red_host[j];
 }

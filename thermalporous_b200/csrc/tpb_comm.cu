@@ -80,7 +80,8 @@ __global__ void pack_planes_kernel(const double* __restrict__ x, long long n, in
 
 // ---- peer-memory kernels ---------------------------------------------------------------------------
 // sum of `count` doubles over the ranks, in rank order (identical bits on every rank); one CTA
-__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PView v, double* buf, int count) {
+// host_out (may be null): pinned host memory that also receives the sums, saving the copy engine's round trip
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PView v, double* buf, int count, double* host_out) {
     __shared__ unsigned long long ep;
     if (threadIdx.x == 0) ep = ++v.epoch[P2P_SLOT_AR];
     __syncthreads();
@@ -101,7 +102,9 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(P2PView v, double* b
         double sum = 0.0;
         for (int r = 0; r < v.nranks; r++) sum += __ldcg(p2p_ar_area(v, v.rank, par, r) + i);
         buf[i] = sum;
+        if (host_out) host_out[i] = sum;
     }
+    if (host_out) __threadfence_system();
 }
 
 // boundary planes of x straight into the neighbours' mailboxes; the last block to finish publishes the epoch
@@ -150,26 +153,7 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(P2PView v, int np, int n
 // then the whole level is copied out of the local mailbox once every section of the epoch has arrived; one CTA
 __global__ void __launch_bounds__(1024) mg_gather_kernel(P2PView v, int hier, double* buf, long long my_off,
                                                          long long my_cnt, long long total) {
-    __shared__ unsigned long long ep;
-    if (threadIdx.x == 0) ep = ++v.epoch[P2P_SLOT_MG + hier];
-    __syncthreads();
-    const unsigned long long e = ep;
-    const int par = (int)(e & 1);
-    for (int r = 0; r < v.nranks; r++) {
-        if (r == v.rank) continue;
-        double* dst = p2p_mg_area(v, r, hier, par) + my_off;
-        for (long long i = threadIdx.x; i < my_cnt; i += blockDim.x) dst[i] = buf[my_off + i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < v.nranks && threadIdx.x != v.rank) {
-        p2p_store_flag(p2p_flag(v, threadIdx.x, P2P_SLOT_MG + hier, v.rank), e);
-        p2p_wait(v, P2P_SLOT_MG + hier, threadIdx.x, e);
-    }
-    __syncthreads();
-    const double* src = p2p_mg_area(v, v.rank, hier, par);
-    for (long long i = threadIdx.x; i < total; i += blockDim.x)
-        if (i < my_off || i >= my_off + my_cnt) buf[i] = __ldcg(src + i);
+    p2p_gather_block(v, hier, buf, my_off, my_cnt, total);
 }
 
 }  // namespace
@@ -184,7 +168,7 @@ struct CommState {
     double* scratch = nullptr;     // nranks doubles
     // peer-memory mailboxes (tpb_internal.cuh)
     bool p2p_ok = false;
-    int p2p_mask = 0;              // TPB_P2P bits: 1 all-reduce, 2 halo, 4 multigrid gather
+    int p2p_mask = 0;              // TPB_P2P bits: 1 all-reduce, 2 halo, 4 multigrid gather, 8 halo fused into SpMV
     char* my_box = nullptr;
     std::vector<char*> peer_box;   // opened IPC mappings (nullptr for this rank)
     unsigned long long* epoch = nullptr;
@@ -253,15 +237,17 @@ void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count) {
 }
 
 // the Krylov / Newton reductions: peer-memory all-reduce when the mailboxes are up, NCCL otherwise
-void tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count) {
-    if (!h->comm || h->comm->nranks == 1) return;
+// returns true when the sums were also stored to host_out (pinned) by the kernel itself
+bool tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count, double* host_out) {
+    if (!h->comm || h->comm->nranks == 1) return false;
     CommState* c = h->comm;
     if (c->p2p_ok && (c->p2p_mask & 1) && count <= P2P_AR_MAX) {
-        p2p_allreduce_kernel<<<1, 256, 0, h->stream>>>(c->view, dev_buf, count);
+        p2p_allreduce_kernel<<<1, 256, 0, h->stream>>>(c->view, dev_buf, count, host_out);
         h->launches++;
-        return;
+        return host_out != nullptr;
     }
     tpb_allreduce_sum(h, dev_buf, count);
+    return false;
 }
 
 // in-place all-gather of one small vector through the mailboxes (the multigrid gather level, once per V-cycle);
@@ -272,6 +258,13 @@ bool tpb_p2p_gather(tpb_handle_s* h, int hier, double* buf, long long my_off, lo
     if (total > c->view.mg_cap || hier < 0 || hier > 1) return false;
     mg_gather_kernel<<<1, 1024, 0, h->stream>>>(c->view, hier, buf, my_off, my_cnt, total);
     h->launches++;
+    return true;
+}
+
+bool tpb_p2p_halo(tpb_handle_s* h, P2PView* v, unsigned int** tickets) {
+    if (!h->comm || !h->comm->p2p_ok || (h->comm->p2p_mask & 10) != 10) return false;
+    *v = h->comm->view;
+    *tickets = h->comm->ticket + 1;
     return true;
 }
 
@@ -290,10 +283,11 @@ void tpb_p2p_check(tpb_handle_s* h) {
 }
 
 // Set up the mailboxes: allocate, exchange the CUDA IPC handles over NCCL, map the peers' boxes.  Any failure (IPC
-// not permitted in this container, no peer access) leaves the NCCL paths in charge.  TPB_P2P=0 disables, default 7.
+// not permitted in this container, no peer access) leaves the NCCL paths in charge.  TPB_P2P=0 disables, default 15
+// (1 Krylov all-reduce, 2 halo planes, 4 multigrid gather, 8 halo fused into the SpMV kernel).
 static void p2p_init(tpb_handle_s* h) {
     CommState* c = h->comm;
-    const int mask = getenv("TPB_P2P") ? atoi(getenv("TPB_P2P")) : 7;
+    const int mask = getenv("TPB_P2P") ? atoi(getenv("TPB_P2P")) : 15;
     if (mask == 0 || c->nranks < 2 || c->nranks > P2P_MAXR) return;
     NcclApi& a = api();
     P2PView& v = c->view;
@@ -356,10 +350,10 @@ static void p2p_init(tpb_handle_s* h) {
     if (me[0] != 0.0) return;   // some rank could not map a peer: NCCL paths stay in charge
     c->epoch = tpb_dalloc<unsigned long long>(P2P_NSLOT);
     c->err = tpb_dalloc<int>(1);
-    c->ticket = tpb_dalloc<unsigned int>(1);
+    c->ticket = tpb_dalloc<unsigned int>(4);   // [0] push/pull kernels, [1..3] fused halo kernels
     TPB_CUDA(cudaMemset(c->epoch, 0, P2P_NSLOT * sizeof(unsigned long long)));
     TPB_CUDA(cudaMemset(c->err, 0, sizeof(int)));
-    TPB_CUDA(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+    TPB_CUDA(cudaMemset(c->ticket, 0, 4 * sizeof(unsigned int)));
     v.epoch = c->epoch;
     v.err = c->err;
     c->p2p_mask = mask;

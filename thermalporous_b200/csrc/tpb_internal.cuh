@@ -114,7 +114,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
 constexpr int P2P_MAXR = 16;        // ranks
 constexpr int P2P_AR_MAX = 256;     // doubles per all-reduce
 enum { P2P_SLOT_AR = 0, P2P_SLOT_HALO_LO = 1, P2P_SLOT_HALO_HI = 2, P2P_SLOT_MG = 3 /* + hierarchy (0|1) */, P2P_NSLOT = 8 };
-constexpr long long P2P_SPIN_MAX = 4000000;   // ~ seconds
+constexpr long long P2P_SPIN_MAX = 4000000;   // with the back-off in p2p_wait: tens of seconds
 
 struct P2PView {
     char* box[P2P_MAXR];            // box[r]: rank r's mailbox as mapped in this process
@@ -141,7 +141,7 @@ __device__ __forceinline__ bool p2p_wait(const P2PView& v, int slot, int src, un
     const unsigned long long* f = p2p_flag(v, v.rank, slot, src);
     for (long long spin = 0; spin < P2P_SPIN_MAX; spin++) {
         if (p2p_load_flag(f) >= e) return true;
-        __nanosleep(64);
+        __nanosleep(spin < 4096 ? 32 : 4000);   // a peer that is merely late (allocation, graph instantiation) gets ~ 20 s
     }
     atomicExch(v.err, 1);
     return false;
@@ -155,8 +155,37 @@ __device__ __forceinline__ double* p2p_halo_area(const P2PView& v, int r, bool f
 __device__ __forceinline__ double* p2p_mg_area(const P2PView& v, int r, int hier, int par) {
     return reinterpret_cast<double*>(v.box[r] + v.off_mg) + ((long long)hier * 2 + par) * v.mg_cap;
 }
+// In-place all-gather of a small vector by ONE thread block (the multigrid gather level, <= mg_cap doubles): this
+// rank's section [my_off, my_off + my_cnt) of buf goes into every peer's mailbox, the flags are exchanged, and the
+// peers' sections are copied out of the local mailbox.  Ends with a block barrier: buf is complete for every thread.
+__device__ __forceinline__ void p2p_gather_block(const P2PView& v, int hier, double* buf, long long my_off,
+                                                 long long my_cnt, long long total) {
+    __shared__ unsigned long long s_ep;
+    if (threadIdx.x == 0) s_ep = ++v.epoch[P2P_SLOT_MG + hier];
+    __syncthreads();
+    const unsigned long long e = s_ep;
+    const int par = (int)(e & 1);
+    for (int r = 0; r < v.nranks; r++) {
+        if (r == v.rank) continue;
+        double* dst = p2p_mg_area(v, r, hier, par) + my_off;
+        for (long long i = threadIdx.x; i < my_cnt; i += blockDim.x) dst[i] = buf[my_off + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < v.nranks && threadIdx.x != v.rank) {
+        p2p_store_flag(p2p_flag(v, threadIdx.x, P2P_SLOT_MG + hier, v.rank), e);
+        p2p_wait(v, P2P_SLOT_MG + hier, threadIdx.x, e);
+    }
+    __syncthreads();
+    const double* src = p2p_mg_area(v, v.rank, hier, par);
+    for (long long i = threadIdx.x; i < total; i += blockDim.x)
+        if (i < my_off || i >= my_off + my_cnt) buf[i] = __ldcg(src + i);
+    __syncthreads();
+}
 // true (and *v filled) when the handle has working mailboxes; `want` = bit of TPB_P2P (1 all-reduce, 2 halo, 4 multigrid)
 bool tpb_p2p_view(tpb_handle_s* h, int want, P2PView* v);
+// mailboxes + the three ticket counters of the fused halo kernels (TPB_P2P bit 8; needs bit 2); false = unfused path
+bool tpb_p2p_halo(tpb_handle_s* h, P2PView* v, unsigned int** tickets);
 bool tpb_p2p_gather(tpb_handle_s* h, int hier, double* buf, long long my_off, long long my_cnt, long long total);
 void tpb_p2p_check(tpb_handle_s* h);
 int tpb_comm_peer_mode_impl(tpb_handle_s* h);   // throws if a peer-memory wait timed out
@@ -397,7 +426,7 @@ void tpb_launch_assemble(tpb_handle_s* h, const double* u, const double* u_old, 
 void tpb_launch_spmv(tpb_handle_s* h, const double* J, const double* x, double* y);
 void tpb_halo_vector(tpb_handle_s* h, const double* x, int nfields, double* lo, double* hi);
 void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count);
-void tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count);
+bool tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count, double* host_out);
 int tpb_comm_rank(tpb_handle_s* h);
 int tpb_comm_size(tpb_handle_s* h);
 const std::vector<int>& tpb_comm_planes(tpb_handle_s* h);

@@ -797,6 +797,25 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_up_kernel(TailArgs A) {
     cyc_up<NS>(A, A.nlev - 1, 0, (long long)threadIdx.x, (long long)blockDim.x, bar);
 }
 
+// ... or, with the peer-memory mailboxes up and the whole gathered hierarchy inside the single-CTA zone, not cut at
+// all: ONE block restricts down the slab's last levels, all-gathers the gather level's right-hand side through the
+// mailboxes (p2p_gather_block: stores into the peers' HBM, flags, copy-out), runs the gathered levels (redundantly on
+// every rank, identical bits) and prolongs/post-smooths back up - four dependent single-CTA launches become one.
+template <int NS>
+__global__ void __launch_bounds__(TAIL_THREADS) tail_dist_kernel(TailArgs A, TailArgs G, P2PView v, int hier, double* gbuf,
+                                                                 long long my_off, long long my_cnt, long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
+    BlockBarrier bar;
+    const long long tid = threadIdx.x, nth = blockDim.x;
+    cyc_down<NS>(A, 0, A.nlev - 1, tid, nth, bar);
+    p2p_gather_block(v, hier, gbuf, my_off, my_cnt, total);
+    cyc_down<NS>(G, 0, G.nlev - 1, tid, nth, bar);
+    cyc_coarsest<NS>(G, tid, nth, bar);
+    cyc_up<NS>(G, G.nlev - 1, 0, tid, nth, bar);
+    cyc_up<NS>(A, A.nlev - 1, 0, tid, nth, bar);
+}
+
 // ---- K6 / coupling kernels ----------------------------------------------------------------------
 // CPR restriction: rp = x_p - sum_f w_f x_f
 template <int NF>
@@ -1249,14 +1268,14 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     int ltail = m.nlev;
     while (ltail > 0 && m.lev[ltail - 1].n <= TAIL_CELLS) ltail--;
     const int lcoop = std::min(ltail, dist ? last : m.nlev);
-    auto tail_args = [&](int l0) {
+    auto tail_args_of = [&](MgHier& mm, int l0) {
         TailArgs A;
-        A.nlev = m.nlev - l0;
-        for (int l = l0; l < m.nlev; l++) {
-            A.lev[l - l0].g = lg(m.lev[l]);
-            A.lev[l - l0].a = m.lev[l].a;
-            A.lev[l - l0].x = m.lev[l].x;
-            A.lev[l - l0].b = m.lev[l].b;
+        A.nlev = mm.nlev - l0;
+        for (int l = l0; l < mm.nlev; l++) {
+            A.lev[l - l0].g = lg(mm.lev[l]);
+            A.lev[l - l0].a = mm.lev[l].a;
+            A.lev[l - l0].x = mm.lev[l].x;
+            A.lev[l - l0].b = mm.lev[l].b;
         }
         A.pre = pre;
         A.post = o.mg_post;
@@ -1264,6 +1283,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         A.omega = o.mg_overcorrection;
         return A;
     };
+    auto tail_args = [&](int l0) { return tail_args_of(m, l0); };
     for (int l = 0; l < lcoop; l++) {
         MgLevel& L = m.lev[l];
         if (!dist && l == last) {
@@ -1280,6 +1300,14 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
             launch_pdl(tail_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));
             h->launches++;
         }
+    } else if (P2PView pv; m.glob->lev[0].n <= TAIL_CELLS && tpb_p2p_view(h, 4, &pv) &&
+                           m.goff.back() + m.gcnt.back() <= pv.mg_cap) {
+        // slab tail + gather + gathered hierarchy + way back up in one single-CTA kernel (tail_dist_kernel)
+        const int rank = tpb_comm_rank(h);
+        launch_pdl(tail_dist_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(std::min(ltail, last)),
+                   tail_args_of(*m.glob, 0), pv, &m == &h->pc->mg_T ? 1 : 0, m.glob->lev[0].b, m.goff[rank], m.gcnt[rank],
+                   m.goff.back() + m.gcnt.back());
+        h->launches++;
     } else {
         if (ltail < last) {
             launch_pdl(tail_down_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));

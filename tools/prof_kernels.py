@@ -35,5 +35,6 @@ if mode in ("all", "pc"):
     r = eng.stage2_apply(x)
     v = eng.mg_apply(0, x[0].contiguous())
     eng.set_solver_opts(ksp_max_it=4)
-    d = eng.ksp_solve(J, x)   # four Arnoldi steps: multi-dot / multi-axpy
+    eng.pc_setup(J, u, 864.0)   # (set_solver_opts invalidates the set-up)
+    d = eng.ksp_solve(J, x)     # four Arnoldi steps: multi-dot / multi-axpy
 print("ok", mode)
