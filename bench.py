@@ -314,7 +314,7 @@ def run_b200(args):
     eng.pc_setup(J, u, res.dt_vec[-1])
     roof = {}
     # per-launch DRAM traffic from the committed `ncu --set full` captures (profiles/r1_ncu_full_summary.md)
-    traffic = {"spmv": 594.5e6 if n_loc == 1122000 else None, "assemble_FJ": None, "rbgs_fine": 83.1e6 if n_loc == 1122000 else None}
+    traffic = {"spmv": 597.0e6 if n_loc == 1122000 else None, "assemble_FJ": 715.5e6 if n_loc == 1122000 else None, "rbgs_fine": 83.1e6 if n_loc == 1122000 else None}
     for which, name, bpc, units in ((0, "assemble_FJ", BYTES["assemble_FJ"], n_loc), (2, "spmv", BYTES["spmv"], n_loc),
                                     (3, "rbgs_fine", 80, n_loc // 2)):
         t_ms = eng.time_kernel(which, u, uo, res.dt_vec[-1], F, J, x, y, reps=20)
