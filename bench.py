@@ -152,6 +152,12 @@ def cpu_run(nz_layers, steps, warmup, verbose=False):
     eng.set_sources(CS.source_entries(case, prm, geo))
     opts, _, _ = O.resolve(PC, 2)
     eng.set_solver_opts(**opts)
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to its ranks)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    eng.set_num_threads(ncores)
     n = geo.ncell
     u = np.stack([np.full(n, prm.p_ref), np.full(n, prm.T_prod), np.full(n, prm.S_o)])
     uo = u.copy()

@@ -266,6 +266,9 @@ class CpuEngine:
     def num_threads(self):
         return int(self.lib.tpc_num_threads())
 
+    def set_num_threads(self, n):
+        self.lib.tpc_set_num_threads(int(n))
+
 
 def engine_from_problem(pb):
     """Build a CpuEngine from an oracle.tp_oracle.Problem."""

@@ -1554,6 +1554,14 @@ int tpc_get_weights(tpc_handle_s* h, int f, double* out) {
     memcpy(out, h->w[f], sizeof(double) * h->g.n);
     return 0;
 }
+/* launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; the CPU baseline asks for the cores back */
+void tpc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int tpc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
