@@ -1,10 +1,16 @@
-// tpb_comm.cu - slab-partition plumbing: ghost-plane exchange and scalar all-reduces over NCCL.
+// tpb_comm.cu - slab-partition plumbing: ghost-plane exchange, scalar all-reduces and the multigrid gather.
 //
 // Stands in for the MPI traffic PETSc/PyOP2 generate under the reference (halo update before
 // every assembly, MatMult ghost scatter, MPI_Allreduce per Krylov dot).  The path
-// has exactly two exchange patterns: one boundary plane per neighbour (ncclSend/ncclRecv grouped)
-// and a sum of k doubles.  NCCL is resolved at run time with dlopen("libnccl.so.2") - the copy
-// torch already mapped into the process - so the single-GPU library has no NCCL link dependency.
+// has three exchange patterns: one boundary plane per neighbour, a sum of k doubles over all ranks, and an
+// all-gather of the multigrid gather level.  Two transports:
+//   * peer-memory mailboxes (default on one NVLink/NVSwitch node): each rank's mailbox is mapped into every peer
+//     with CUDA IPC and kernels store straight into the receiver's HBM (protocol: tpb_internal.cuh).  Kernels here:
+//     halo_push/halo_pull, p2p_allreduce, mg_gather; the fused forms live with their compute (spmv_halo_kernel in
+//     tpb_spmv.cu, tail_dist_kernel in tpb_pc.cu).
+//   * NCCL (ncclSend/ncclRecv grouped, ncclAllReduce, ncclAllGather): the set-up traffic always, every exchange
+//     when the mailboxes cannot be mapped or TPB_P2P=0.  NCCL is resolved at run time with dlopen("libnccl.so.2")
+//     - the copy torch already mapped into the process - so the single-GPU library has no NCCL link dependency.
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
