@@ -114,6 +114,11 @@ typedef struct {
     double mg_semi_theta;     /* an axis is coarsened on a level only if its mean coupling is at least
                                  theta * the strongest axis' (0 = always coarsen every axis) */
     int mg_full_below;        /* levels with at most this many cells coarsen every axis (0 = never) */
+    double mg_dd_stop;        /* a level whose rows all satisfy sum|off-diagonals| <= mg_dd_stop * |diagonal| is the
+                                 last one: it is solved by a few Gauss-Seidel sweeps (enough for a 1e-3 contraction, at
+                                 most mg_coarse_sweeps) instead of being coarsened - what BoomerAMG's max_row_sum does
+                                 to diagonally dominant rows.  The temperature Schur block is such a matrix while dt
+                                 is small.  0 = never */
     /* second stage: block ILU(0) of the nf x nf block stencil in red-black ordering, one block per
      * rank as PETSc bjacobi+ilu (the slab couplings to other ranks are dropped) */
     int verbose;

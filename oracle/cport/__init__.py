@@ -52,7 +52,8 @@ class SolverOpts(C.Structure):
                 ("stage1", C.c_int), ("decoup", C.c_int), ("schur_pre", C.c_int), ("stage2", C.c_int),
                 ("mg_pre", C.c_int), ("mg_post", C.c_int), ("mg_coarse_sweeps", C.c_int),
                 ("mg_min_cells", C.c_int), ("mg_overcorrection", C.c_double), ("mg_cycles", C.c_int),
-                ("mg_semi_theta", C.c_double), ("mg_full_below", C.c_int), ("verbose", C.c_int)]
+                ("mg_semi_theta", C.c_double), ("mg_full_below", C.c_int), ("mg_dd_stop", C.c_double),
+                ("verbose", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -130,6 +131,7 @@ def default_opts(nphase):
     o.mg_cycles = 1
     o.mg_semi_theta = 0.5
     o.mg_full_below = 0
+    o.mg_dd_stop = 0.1
     o.verbose = 0
     return o
 

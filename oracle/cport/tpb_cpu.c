@@ -65,7 +65,18 @@ typedef struct {
 typedef struct {
     int nlev;
     mglevel lev[MAXLEV];
+    int last_sweeps; /* > 0: the last level is diagonally dominant (mg_dd_stop) and gets this many sweeps */
 } mghier;
+
+/* sweeps for a 1e-3 contraction on a level whose rows have sum|off-diag| <= rho |diag| (csrc/tpb_pc.cu dd_sweeps) */
+static int dd_sweeps(double rho, int cap) {
+    int k = 1;
+    if (rho > 0.0 && rho < 1.0) k = (int)ceil(log(1e-3) / log(rho));
+    if (rho >= 1.0) k = cap;   /* (only reachable with mg_dd_stop >= 1) */
+    if (k < 1) k = 1;
+    if (cap > 0 && k > cap) k = cap;
+    return k;
+}
 
 typedef struct tpc_handle_s {
     cgrid g;
@@ -593,6 +604,7 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
     L->nz = h->g.nz;
     L->n = h->g.n;
     L->a = a0;
+    m->last_sweeps = 0;
     int l = 0;
     for (;;) {
         L = &m->lev[l];
@@ -601,6 +613,22 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
         L->r = (double*)calloc(L->n, sizeof(double));
         L->cx = L->cy = L->cz = 1;
         if (L->n <= o->mg_min_cells || L->n <= 1 || l == MAXLEV - 1) break;
+        if (o->mg_dd_stop > 0.0) {
+            /* strongest row of the level: max over cells of sum|off-diag| / |diag| */
+            double rho = 0.0;
+#pragma omp parallel for reduction(max : rho) schedule(static)
+            for (long c = 0; c < L->n; c++) {
+                double sum = 0.0;
+                for (int s = 1; s < ns; s++) sum += fabs(L->a[(long)s * L->n + c]);
+                const double d = fabs(L->a[c]);
+                const double r = d > 0.0 ? sum / d : (sum > 0.0 ? 1e300 : 0.0);
+                if (r > rho) rho = r;
+            }
+            if (rho <= o->mg_dd_stop) {
+                m->last_sweeps = dd_sweeps(rho, o->mg_coarse_sweeps);
+                break;
+            }
+        }
         /* mean coupling per axis decides which axes are coarsened (semi-coarsening) */
         double m_ax[3] = {0, 0, 0};
         int dims[3] = {L->nx, L->ny, L->nz};
@@ -712,7 +740,7 @@ static void mg_vcycle_level(const tpc_handle_s* h, mghier* m, int l) {
     const int ns = h->g.ns;
     mglevel* L = &m->lev[l];
     if (l == m->nlev - 1) {
-        int sweeps = o->mg_coarse_sweeps > 0 ? o->mg_coarse_sweeps : 1;
+        int sweeps = m->last_sweeps > 0 ? m->last_sweeps : (o->mg_coarse_sweeps > 0 ? o->mg_coarse_sweeps : 1);
         for (int s = 0; s < sweeps; s++) mg_rbgs(L, ns, L->b, L->x, s == 0);
         return;
     }

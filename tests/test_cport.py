@@ -50,6 +50,36 @@ def test_pc_is_a_fixed_linear_operator_and_reduces_the_residual():
     eng.close()
 
 
+def test_diagonally_dominant_levels_end_the_hierarchy():
+    """mg_dd_stop: with a small time step the temperature Schur block is accumulation-dominated (rows with
+    sum|off-diagonals| << |diagonal|) and needs no coarse levels - a few sweeps replace its V-cycle; the pressure block
+    is elliptic and keeps its hierarchy.  The Newton solve is the same solve either way."""
+    pb, u, uo = random_problem(3, 2, (8, 10, 12), seed=4, spread=0.02)
+    res = {}
+    for dd in (0.1, 0.0):
+        eng = cport.engine_from_problem(pb)
+        eng.set_solver_opts(stage1=cport.S1_CPTR, decoup=1, mg_dd_stop=dd, snes_rtol=1e-11, snes_stol=1e-13)
+        F, J = eng.assemble(u, uo, 5.0)
+        eng.pc_setup(J, u, 5.0)
+        lp, lT = eng.mg_levels(0), eng.mg_levels(1)
+        A = eng.mg_level_op(1, 0)
+        rho = (np.abs(A[1:]).sum(axis=0) / np.abs(A[0])).max()
+        b = np.random.default_rng(3).normal(size=A.shape[1])
+        y = eng.mg_apply(1, b)
+        # residual of the T solve b - A y on the structured stencil, through the engine's own operator: use the Newton solve below
+        un = u.copy()
+        st = eng.newton_solve(un, uo.copy(), 5.0)
+        res[dd] = (len(lp), len(lT), rho, y, un, st.nits, st.lits)
+        eng.close()
+    on, off = res[0.1], res[0.0]
+    assert on[2] < 0.1 and on[1] == 1 and off[1] > 1          # T: one level when the rule is on
+    assert on[0] == off[0] or on[0] < off[0]                 # p: never more levels
+    assert np.abs(on[3] - off[3]).max() <= 1e-3 * np.abs(off[3]).max()   # the sweeps solve the block as well as the V-cycle
+    assert on[5] == off[5] and abs(on[6] - off[6]) <= 2      # same Newton count, Krylov count within 2
+    for f in range(3):
+        assert np.abs(on[4][f] - off[4][f]).max() <= 1e-8 * np.abs(off[4][f]).max()
+
+
 def test_galerkin_coarse_operators_preserve_row_sums():
     """piecewise-constant Galerkin: the sum of all entries of a level equals that of the level above."""
     pb, u, uo = random_problem(3, 2, (9, 10, 11), seed=3, spread=0.05)

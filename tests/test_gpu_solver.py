@@ -42,6 +42,10 @@ COMBOS = [
     (2, 2, (1, 1, 1), dict(stage1=cport.S1_CPTR)),
     (2, 3, (3, 3, 3), dict(stage1=cport.S1_CPTR, mg_pre=1, mg_post=0, mg_coarse_sweeps=1)),
     (2, 3, (17, 19, 23), dict(stage1=cport.S1_CPTR, decoup=2, mg_semi_theta=0.0, mg_full_below=100)),
+    # diagonal-dominance stop of the hierarchies: never | at any level whose rows pass 0.5 | always at level 0
+    (2, 3, (9, 11, 14), dict(stage1=cport.S1_CPTR, decoup=0, mg_dd_stop=0.0)),
+    (2, 3, (9, 11, 14), dict(stage1=cport.S1_CPTR, decoup=1, mg_dd_stop=0.5)),
+    (2, 3, (6, 13, 10), dict(stage1=cport.S1_CPTR, decoup=1, mg_dd_stop=1e9)),
 ]
 TOL = 1e-10
 

@@ -42,7 +42,8 @@ class SolverOpts(C.Structure):
                 ("stage1", C.c_int), ("decoup", C.c_int), ("schur_pre", C.c_int), ("stage2", C.c_int),
                 ("mg_pre", C.c_int), ("mg_post", C.c_int), ("mg_coarse_sweeps", C.c_int),
                 ("mg_min_cells", C.c_int), ("mg_overcorrection", C.c_double), ("mg_cycles", C.c_int),
-                ("mg_semi_theta", C.c_double), ("mg_full_below", C.c_int), ("verbose", C.c_int)]
+                ("mg_semi_theta", C.c_double), ("mg_full_below", C.c_int), ("mg_dd_stop", C.c_double),
+                ("verbose", C.c_int)]
 
 
 class Stats(C.Structure):

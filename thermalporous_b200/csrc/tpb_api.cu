@@ -325,6 +325,7 @@ int tpb_solver_defaults(int nphase, tpb_solver_opts* o) {
     o->mg_cycles = 1;
     o->mg_semi_theta = 0.5;
     o->mg_full_below = 0;
+    o->mg_dd_stop = 0.1;
     o->verbose = 0;
     return TPB_OK;
 }

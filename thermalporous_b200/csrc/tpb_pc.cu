@@ -54,7 +54,18 @@ struct MgHier {
     double* ga = nullptr;          // gathered operator of the gather level (ns * gn)
     long long ga_cap = 0;
     std::vector<long long> gcnt, goff;   // cells of every rank on the gather level and their offsets
+    int last_sweeps = 0;           // > 0: the last level is diagonally dominant (mg_dd_stop) and gets this many sweeps
 };
+
+// sweeps for a 1e-3 contraction on a level whose rows have sum|off-diag| <= rho |diag| (same rule in oracle/cport)
+inline int dd_sweeps(double rho, int cap) {
+    int k = 1;
+    if (rho > 0.0 && rho < 1.0) k = (int)ceil(log(1e-3) / log(rho));
+    if (rho >= 1.0) k = cap;   // (only reachable with mg_dd_stop >= 1)
+    if (k < 1) k = 1;
+    if (cap > 0 && k > cap) k = cap;
+    return k;
+}
 
 }  // namespace
 
@@ -409,15 +420,31 @@ __device__ __forceinline__ long long nbr_clamped(int nx, int ny, int nz, int i, 
     }
 }
 
-// sum over cells of |a[2ax+1]| + |a[2ax+2]| for the three axes -> out[0..2] (atomics; a few thousand adds)
+// sum over cells of |a[2ax+1]| + |a[2ax+2]| for the three axes -> out[0..2] (atomics; a few thousand adds), and the
+// strongest row of the level, max over cells of sum|off-diagonals| / |diagonal| -> out[3] (mg_dd_stop; summed in
+// slot order and divided exactly as oracle/cport does, a maximum has no order: the two agree to the bit)
 template <int NS>
 __global__ void __launch_bounds__(256) strength_kernel(const double* __restrict__ a, long long n, double* out) {
     double acc[3] = {0.0, 0.0, 0.0};
+    double rho = 0.0;
     for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        double v[NS];
+        double sum = 0.0;
 #pragma unroll
-        for (int ax = 0; ax < (NS - 1) / 2; ax++)
-            acc[ax] += fabs(a[(long long)(2 * ax + 1) * n + c]) + fabs(a[(long long)(2 * ax + 2) * n + c]);
+        for (int s = 1; s < NS; s++) {
+            v[s] = fabs(a[(long long)s * n + c]);
+            sum += v[s];
+        }
+#pragma unroll
+        for (int ax = 0; ax < (NS - 1) / 2; ax++) acc[ax] += v[2 * ax + 1] + v[2 * ax + 2];
+        const double d = fabs(a[c]);
+        const double r = d > 0.0 ? sum / d : (sum > 0.0 ? 1e300 : 0.0);
+        rho = fmax(rho, r);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rho = fmax(rho, __shfl_down_sync(0xffffffffu, rho, o));
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(out + 3), (unsigned long long)__double_as_longlong(rho));
     __shared__ double sm[3][8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -1147,14 +1174,20 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
         }
         const long long stop_at = dist ? std::max<long long>(gather_cells(), o.mg_min_cells) : o.mg_min_cells;
         if (nglob <= stop_at || nglob <= 1 || l == MAXLEV - 1) break;
-        TPB_CUDA(cudaMemsetAsync(pc->strength, 0, 3 * sizeof(double), h->stream));
+        TPB_CUDA(cudaMemsetAsync(pc->strength, 0, 4 * sizeof(double), h->stream));
         unsigned blocks = std::min<unsigned>(nblk(L.n, 256), 1184u);
         strength_kernel<NS><<<blocks, 256, 0, h->stream>>>(L.a, L.n, pc->strength);
         h->launches++;
         if (dist) tpb_allreduce_sum(h, pc->strength, 3);
-        double m_ax[3];
-        TPB_CUDA(cudaMemcpyAsync(m_ax, pc->strength, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        double m_ax[4];
+        TPB_CUDA(cudaMemcpyAsync(m_ax, pc->strength, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         TPB_CUDA(cudaStreamSynchronize(h->stream));
+        // a diagonally dominant level is the last one (tpb_solver_opts.mg_dd_stop).  Single-rank handles only in r1:
+        // on slabs the decision would have to be agreed between the ranks and a stopped hierarchy skip its gather level
+        if (o.mg_dd_stop > 0.0 && tpb_comm_size(h) == 1 && m_ax[3] <= o.mg_dd_stop) {
+            nw.last_sweeps = dd_sweeps(m_ax[3], o.mg_coarse_sweeps);
+            break;
+        }
         double mmax = 0.0;
         for (int ax = 0; ax < 3; ax++)
             if (dims[ax] > 1 && m_ax[ax] > mmax) mmax = m_ax[ax];
@@ -1186,6 +1219,7 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
     nw.nlev = l + 1;
     mg_free_levels(old);
     m.nlev = nw.nlev;
+    m.last_sweeps = nw.last_sweeps;
     for (int q = 0; q < MAXLEV; q++) m.lev[q] = q < nw.nlev ? nw.lev[q] : MgLevel();
     TPB_CUDA(cudaGetLastError());
 }
@@ -1261,7 +1295,8 @@ template <int NS>
 void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     const tpb_solver_opts& o = h->opts;
     const int pre = o.mg_pre > 0 ? o.mg_pre : 1;
-    const int coarse = o.mg_coarse_sweeps > 0 ? o.mg_coarse_sweeps : 1;
+    const int coarse_opt = o.mg_coarse_sweeps > 0 ? o.mg_coarse_sweeps : 1;
+    const int coarse = m.last_sweeps > 0 ? m.last_sweeps : coarse_opt;
     const bool dist = m.glob != nullptr;   // the last level is the gather level: smoothed as level 0 of m.glob
     const int last = m.nlev - 1;
     // level zones: [0, lcoop) one kernel per colour pass, [ltail, last] inside one CTA (levels <= TAIL_CELLS)
@@ -1279,7 +1314,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         }
         A.pre = pre;
         A.post = o.mg_post;
-        A.coarse_sweeps = coarse;
+        A.coarse_sweeps = mm.last_sweeps > 0 ? mm.last_sweeps : coarse_opt;
         A.omega = o.mg_overcorrection;
         return A;
     };
@@ -1639,7 +1674,7 @@ void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double
         h->pc->t1 = tpb_dalloc<double>(nd);
         h->pc->t2 = tpb_dalloc<double>(nd);
         h->pc->t3 = tpb_dalloc<double>(nd);
-        h->pc->strength = tpb_dalloc<double>(3);
+        h->pc->strength = tpb_dalloc<double>(4);
     }
     h->pc->J = J;
     DISPATCH(pc_setup_t, h, J, u, dt);
