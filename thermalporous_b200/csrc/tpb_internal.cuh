@@ -427,6 +427,7 @@ void tpb_launch_spmv(tpb_handle_s* h, const double* J, const double* x, double* 
 void tpb_halo_vector(tpb_handle_s* h, const double* x, int nfields, double* lo, double* hi);
 void tpb_allreduce_sum(tpb_handle_s* h, double* dev_buf, int count);
 bool tpb_allreduce_sum_hot(tpb_handle_s* h, double* dev_buf, int count, double* host_out);
+void tpb_allreduce_max(tpb_handle_s* h, double* dev_buf, int count);
 int tpb_comm_rank(tpb_handle_s* h);
 int tpb_comm_size(tpb_handle_s* h);
 const std::vector<int>& tpb_comm_planes(tpb_handle_s* h);

@@ -55,7 +55,16 @@ struct MgHier {
     long long ga_cap = 0;
     std::vector<long long> gcnt, goff;   // cells of every rank on the gather level and their offsets
     int last_sweeps = 0;           // > 0: the last level is diagonally dominant (mg_dd_stop) and gets this many sweeps
+    bool skip_glob = false;        // multi-rank hierarchy that stopped on diagonal dominance: no gather level this set-up
 };
+
+// mg_dd_stop on multi-rank slabs (TPB_MG_DD_DIST=1; off until it has been run on more than one GPU): the row ratio is
+// max-reduced over the ranks, so all of them stop at the same level, and a hierarchy that stopped this way has no
+// gather level - its last level is smoothed slab by slab like the levels above it
+inline bool dd_on_slabs() {
+    static const bool v = getenv("TPB_MG_DD_DIST") && atoi(getenv("TPB_MG_DD_DIST")) != 0;
+    return v;
+}
 
 // sweeps for a 1e-3 contraction on a level whose rows have sum|off-diag| <= rho |diag| (same rule in oracle/cport)
 inline int dd_sweeps(double rho, int cap) {
@@ -1179,12 +1188,13 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
         strength_kernel<NS><<<blocks, 256, 0, h->stream>>>(L.a, L.n, pc->strength);
         h->launches++;
         if (dist) tpb_allreduce_sum(h, pc->strength, 3);
+        if (dist && dd_on_slabs()) tpb_allreduce_max(h, pc->strength + 3, 1);
         double m_ax[4];
         TPB_CUDA(cudaMemcpyAsync(m_ax, pc->strength, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         TPB_CUDA(cudaStreamSynchronize(h->stream));
         // a diagonally dominant level is the last one (tpb_solver_opts.mg_dd_stop).  Single-rank handles only in r1:
         // on slabs the decision would have to be agreed between the ranks and a stopped hierarchy skip its gather level
-        if (o.mg_dd_stop > 0.0 && tpb_comm_size(h) == 1 && m_ax[3] <= o.mg_dd_stop) {
+        if (o.mg_dd_stop > 0.0 && (tpb_comm_size(h) == 1 || dd_on_slabs()) && m_ax[3] <= o.mg_dd_stop) {
             nw.last_sweeps = dd_sweeps(m_ax[3], o.mg_coarse_sweeps);
             break;
         }
@@ -1233,7 +1243,8 @@ void mg_setup_t(tpb_handle_s* h, MgHier& m, double* a0) {
     row_repair_kernel<NS><<<nblk(h->g.n, 256), 256, 0, h->stream>>>(a0, h->g.n);
     h->launches++;
     mg_coarsen_t<NS>(h, m, a0, h->g.nx, h->g.ny, h->g.nz, dist, planes);
-    if (!dist) return;
+    m.skip_glob = dist && m.last_sweeps > 0;   // (only with dd_on_slabs(): otherwise last_sweeps stays 0 on slabs)
+    if (!dist || m.skip_glob) return;
     // ---- gather level: concatenate the ranks' last levels along the slab axis ----------------------
     const int rank = tpb_comm_rank(h);
     MgLevel& L = m.lev[m.nlev - 1];
@@ -1297,7 +1308,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     const int pre = o.mg_pre > 0 ? o.mg_pre : 1;
     const int coarse_opt = o.mg_coarse_sweeps > 0 ? o.mg_coarse_sweeps : 1;
     const int coarse = m.last_sweeps > 0 ? m.last_sweeps : coarse_opt;
-    const bool dist = m.glob != nullptr;   // the last level is the gather level: smoothed as level 0 of m.glob
+    const bool dist = m.glob != nullptr && !m.skip_glob;   // the last level is the gather level: smoothed as level 0 of m.glob
     const int last = m.nlev - 1;
     // level zones: [0, lcoop) one kernel per colour pass, [ltail, last] inside one CTA (levels <= TAIL_CELLS)
     int ltail = m.nlev;
@@ -1381,7 +1392,7 @@ template <int NS>
 void mg_apply_t(tpb_handle_s* h, MgHier& m, const double* b, double* y) {
     MgLevel& L = m.lev[0];
     const int cycles = h->opts.mg_cycles > 0 ? h->opts.mg_cycles : 1;
-    if (m.glob && m.nlev == 1) {
+    if (m.glob && !m.skip_glob && m.nlev == 1) {
         // level 0 is itself the gather level (small grids on several ranks): its vectors are sections of the
         // gathered level, so copy in and out
         tpb_copy(h, (size_t)L.n, b, L.b);
