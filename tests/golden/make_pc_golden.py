@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Generate tests/golden/pc_decoup.npz by running the reference's OWN decoupling algebra.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_pc_golden.py
+
+thermalporous/preconditioners.py builds its CPR / CPTR first stages from PETSc Mat/Vec calls on sub-blocks of the
+assembled Jacobian: `CPRStage1PC.create_decoup_{QI,TI,QI_temp,TI_temp}` (preconditioners.py:684-873) and
+`CPTRStage1PC.create_decoup_{QI,TI}` (:1445-1543).  Those methods are executed here UNMODIFIED: the module is imported
+over tests/golden/fd_shim (whose firedrake.petsc implements the needed slice of petsc4py on scipy.sparse), an
+instance is made without running `initialize` (which needs Firedrake's assembler), its `*mat` attributes are set to
+the sub-blocks of a golden Jacobian (tests/golden/g*.npz, made by the reference's form code), and the method is
+called.  What it leaves in `apsinvdss` / `Atildepp` (`a0sinvdss` / `Atilde00`) - the restriction weights and the
+decoupled pressure operator - is stored in block-stencil layout next to the inputs' names.
+
+The fixture travels to the GPU box; this script and the shim do not need to.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "fd_shim"))
+sys.path.insert(0, os.environ.get("TPB_REFERENCE", "/root/reference"))
+sys.path.insert(0, ROOT)
+
+from firedrake.petsc import PETSc  # noqa: E402  (the shim)
+from thermalporous import preconditioners as ref  # noqa: E402  (the reference, unmodified)
+from oracle import tp_oracle as orc  # noqa: E402
+from tests.golden_util import load  # noqa: E402
+
+
+def blocks(J, g):
+    """field-ordered sub-blocks A[f][c] (each n x n, scipy CSR) of a block-stencil Jacobian"""
+    A = orc.to_csr(J, g, "field").tocsr()
+    nf, n = J.shape[1], J.shape[3]
+    return [[A[f * n:(f + 1) * n, c * n:(c + 1) * n] for c in range(nf)] for f in range(nf)], n
+
+
+def to_stencil(M, g):
+    """n x n sparse matrix with the grid's 5|7-point pattern -> a[s][cell]"""
+    M = sp.csr_matrix(M)
+    n = M.shape[0]
+    cells = np.arange(n)
+    ii, jj, kk = cells % g.nx, (cells // g.nx) % g.ny, cells // (g.nx * g.ny)
+    offs = orc.stencil_offsets(g)
+    out = np.zeros((len(offs), n))
+    for s, (di, dj, dk) in enumerate(offs):
+        ni, nj, nk = ii + di, jj + dj, kk + dk
+        ok = (ni >= 0) & (ni < g.nx) & (nj >= 0) & (nj < g.ny) & (nk >= 0) & (nk < g.nz)
+        nb = (ni + g.nx * (nj + g.ny * nk))[ok]
+        out[s, ok] = np.asarray(M[cells[ok], nb]).ravel()
+    # nothing outside the stencil
+    assert abs(abs(M).sum() - np.abs(out).sum()) <= 1e-9 * abs(M).sum()
+    return out
+
+
+def cpr(B, n, decoup, two_phase):
+    """CPRStage1PC: p = field 0, s = the last field (T single-phase, S_o two-phase); *_temp: nonp = (T, S_o)"""
+    pc = object.__new__(ref.CPRStage1PC)
+    pc.decoup = decoup
+    pc.Appmat = PETSc.Mat(B[0][0])
+    s = 2 if two_phase else 1
+    if decoup.endswith("temp"):
+        T, S = 1, 2
+        pc.Assmat = PETSc.Mat(sp.bmat([[B[T][T], B[T][S]], [B[S][T], B[S][S]]]))
+        pc.Aspmat = PETSc.Mat(sp.bmat([[B[T][0]], [B[S][0]]]))
+        pc.Apsmat = PETSc.Mat(sp.bmat([[B[0][T], B[0][S]]]))
+        pc.ASSmat, pc.ASTmat = PETSc.Mat(B[S][S]), PETSc.Mat(B[S][T])
+        pc.ATSmat, pc.ATTmat = PETSc.Mat(B[T][S]), PETSc.Mat(B[T][T])
+        pc.ApSmat, pc.ApTmat = PETSc.Mat(B[0][S]), PETSc.Mat(B[0][T])
+        # W22 = V*V field index sets (preconditioners.py:443-451): T dofs first, then S_o
+        pc.TT_is, pc.SS_is, pc.pp_is = PETSc.IS(np.arange(n)), PETSc.IS(np.arange(n, 2 * n)), PETSc.IS(np.arange(n))
+    else:
+        pc.Assmat, pc.Aspmat, pc.Apsmat = PETSc.Mat(B[s][s]), PETSc.Mat(B[s][0]), PETSc.Mat(B[0][s])
+    getattr(pc, "create_decoup_" + decoup)(None)
+    W = sp.csr_matrix(pc.apsinvdss.m)
+    if decoup.endswith("temp"):
+        w = np.stack([W[np.arange(n), np.arange(n)].A1, W[np.arange(n), n + np.arange(n)].A1])   # w_T, w_S
+    else:
+        w = W.diagonal()[None, :]
+        assert abs(abs(W).sum() - np.abs(w).sum()) <= 1e-12 * abs(W).sum()
+    return w, pc.Atildepp.m
+
+
+def cptr(B, n, decoup):
+    """CPTRStage1PC: '0' = (p, T) interleaved as the reference's D0s indexing (2i, 2i+1) assumes, s = S_o"""
+    il = np.empty(2 * n, dtype=np.int64)
+    il[0::2], il[1::2] = np.arange(n), n + np.arange(n)          # interleaved position -> field-ordered position
+    P = sp.csr_matrix((np.ones(2 * n), (np.arange(2 * n), il)), shape=(2 * n, 2 * n))
+    A00 = P @ sp.bmat([[B[0][0], B[0][1]], [B[1][0], B[1][1]]]).tocsr() @ P.T
+    A0s = P @ sp.bmat([[B[0][2]], [B[1][2]]]).tocsr()
+    As0 = sp.bmat([[B[2][0], B[2][1]]]).tocsr() @ P.T
+    pc = object.__new__(ref.CPTRStage1PC)
+    pc.decoup = decoup
+    pc.A00mat, pc.A0smat, pc.As0mat, pc.Assmat = PETSc.Mat(A00), PETSc.Mat(A0s), PETSc.Mat(As0), PETSc.Mat(B[2][2])
+    pc.A0smat.setBlockSizes(2, 1)
+    getattr(pc, "create_decoup_" + decoup)(None)
+    W = sp.csr_matrix(pc.a0sinvdss.m)
+    w = np.stack([W[2 * np.arange(n), np.arange(n)].A1, W[2 * np.arange(n) + 1, np.arange(n)].A1])   # w_p, w_T
+    At = sp.csr_matrix(pc.Atilde00.m)
+    return w, At[0::2, 0::2]
+
+
+def main():
+    out = {}
+    for name, two_phase in (("g2_sp2d_hetero_peaceman", False), ("g3_tp2d_hetero_peaceman", True),
+                            ("g5_tp3d_hetero_wellheater", True)):
+        meta, pb, z = load(name)
+        g = pb.grid
+        B, n = blocks(z["J"], g)
+        todo = [("cpr", d) for d in (("QI", "TI", "QI_temp", "TI_temp") if two_phase else ("QI", "TI"))]
+        if two_phase:
+            todo += [("cptr", "QI"), ("cptr", "TI")]
+        for kind, decoup in todo:
+            w, At = cpr(B, n, decoup, two_phase) if kind == "cpr" else cptr(B, n, decoup)
+            key = "%s|%s|%s" % (name, kind, decoup)
+            out[key + "|w"] = w
+            out[key + "|App"] = to_stencil(At, g)
+            print("%-48s weights %s  |w|max %.3e   App~ %s" % (key, w.shape, np.abs(w).max(), out[key + "|App"].shape))
+    path = os.path.join(HERE, "pc_decoup.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.0f kB" % (os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    main()
