@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generate tests/golden/pc_decoup.npz by running the reference's OWN decoupling algebra.
+"""Generate tests/golden/pc/decoup.npz by running the reference's OWN decoupling algebra.
 
 Run in the build container only (needs /root/reference):
 
@@ -122,7 +122,8 @@ def main():
             out[key + "|w"] = w
             out[key + "|App"] = to_stencil(At, g)
             print("%-48s weights %s  |w|max %.3e   App~ %s" % (key, w.shape, np.abs(w).max(), out[key + "|App"].shape))
-    path = os.path.join(HERE, "pc_decoup.npz")
+    os.makedirs(os.path.join(HERE, "pc"), exist_ok=True)
+    path = os.path.join(HERE, "pc", "decoup.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "%.0f kB" % (os.path.getsize(path) / 1e3))
 

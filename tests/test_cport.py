@@ -183,7 +183,7 @@ def test_free_running_time_loop(name):
 def _pc_decoup_cases():
     import os
     from tests.golden_util import GOLDEN_DIR
-    z = np.load(os.path.join(GOLDEN_DIR, "pc_decoup.npz"))
+    z = np.load(os.path.join(GOLDEN_DIR, "pc", "decoup.npz"))
     return sorted({k.rsplit("|", 1)[0] for k in z.files})
 
 
@@ -194,7 +194,7 @@ def test_decoupling_matches_the_references_own_algebra(key):
     petsc4py shim by tests/golden/make_pc_golden.py."""
     import os
     from tests.golden_util import GOLDEN_DIR
-    fix = np.load(os.path.join(GOLDEN_DIR, "pc_decoup.npz"))
+    fix = np.load(os.path.join(GOLDEN_DIR, "pc", "decoup.npz"))
     name, kind, decoup = key.split("|")
     meta, pb, z = load(name)
     eng = cport.engine_from_problem(pb)
