@@ -382,8 +382,16 @@ def TestFunction(V):
     return _Test(0)
 
 
+_TRIALS = []
+
+
 def TrialFunction(V):
-    raise NotImplementedError("trial functions are not needed for residual evaluation")
+    """A Function standing for the trial argument of a bilinear form that is LINEAR in it: firedrake.assemble's
+    create_assembly_callable (shim) recovers the matrix by evaluating the form on indicator functions of a distance-2
+    colouring.  Only the scalar DG0 space is needed (preconditioners.py:35,189)."""
+    t = Function(V, name="trial")
+    _TRIALS.append(t)
+    return t
 
 
 class _Coords(Node):
@@ -826,7 +834,9 @@ class NonlinearVariationalSolver:
 
 
 class PCBase:
-    pass
+    def get_appctx(self, pc):
+        # Firedrake hands a python PC the solver's appctx (plus "state" = the current iterate) through the DM
+        return pc.appctx
 
 
 class File:
@@ -856,3 +866,15 @@ def MeshHierarchy(*a, **k):
 
 def ExtrudedMeshHierarchy(*a, **k):
     raise NotImplementedError
+
+
+def inner(a, b):
+    """scalar DG0 arguments only (imported by preconditioners.py:13, unused there)"""
+    return a * b
+
+
+# `firedrake.assemble` is both a function (above) and a sub-module (`from firedrake.assemble import allocate_matrix`,
+# preconditioners.py:14): importing the sub-module rebinds the package attribute, so the function is put back after it
+_assemble_fn = assemble
+from . import assemble as _assemble_mod  # noqa: E402,F401
+assemble = _assemble_fn

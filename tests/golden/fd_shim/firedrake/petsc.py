@@ -150,7 +150,13 @@ class _IS:
         return int(self.indices.size)
 
 
+class _Options:
+    def getString(self, name, default=None):
+        return default
+
+
 class PETSc:
     Mat = _Mat
     Vec = _Vec
     IS = _IS
+    Options = _Options

@@ -14,6 +14,12 @@ the sub-blocks of a golden Jacobian (tests/golden/g*.npz, made by the reference'
 called.  What it leaves in `apsinvdss` / `Atildepp` (`a0sinvdss` / `Atilde00`) - the restriction weights and the
 decoupled pressure operator - is stored in block-stencil layout next to the inputs' names.
 
+The temperature Schur approximation is recorded the same way: `ConvDiffSchurPC.initialize` /
+`ConvDiffSchurTwoPhasesPC.initialize` (:11-118, :165-286) build their frozen-coefficient convection-diffusion form
+from the model's state and assemble it; over the shim the form is evaluated by the DG0 evaluator that produces the
+residual fixtures (fd_shim/firedrake/assemble.py) and the assembled operator is stored.  The models are rebuilt from
+the residual fixtures' own inputs (fields, parameters, state, dt) with the well/heater set-ups of make_golden.py.
+
 The fixture travels to the GPU box; this script and the shim do not need to.
 """
 import os
@@ -106,8 +112,70 @@ def cptr(B, n, decoup):
     return w, At[0::2, 0::2]
 
 
+class _FakePC:
+    """what initialize() asks of the PETSc PC before it assembles"""
+
+    def __init__(self, appctx):
+        self.appctx = appctx
+
+    def getOptionsPrefix(self):
+        return "fieldsplit_1_"
+
+    def getOperators(self):
+        return None, None
+
+
+def convdiff(name):
+    """rebuild the reference model of a residual fixture and let the reference's PC class assemble its operator"""
+    import firedrake as fd
+    from firedrake.assemble import Assembled
+    import make_golden as mg
+    meta, pb, z = load(name)
+    g = pb.grid
+    prm = mg.fresh_params(**meta["params"])
+    shape = (g.nz, g.ny, g.nx)
+    fields = tuple(np.asarray(z[k]).reshape(shape) if z[k].size else None for k in ("phi", "Kx", "Ky", "Kz"))
+    two = meta["nphase"] == 2
+    Model = mg.TwoPhase if two else mg.SinglePhase
+    if g.dim == 2:
+        geo = mg.HeteroGeo2D(g.nx, g.ny, prm, fields, dx=g.dx, dy=g.dy)
+        pts_p, pts_i = [[2.3 * 6.096, 4.6 * 3.048]], [[9.4 * 6.096, 7.2 * 3.048]]
+        case = mg.WellCase(prm, geo, prod_points=pts_p, inj_points=pts_i)
+    else:
+        geo = mg.HeteroGeo3D(g.nx, g.ny, g.nz, prm, fields, dx=g.dx, dy=g.dy, dz=g.dz)
+        pp = [[1.5 * 6.096, 2.5 * 3.048, 0.5 * 0.6096]]
+        ip = [[4.5 * 6.096, 1.5 * 3.048, 3.5 * 0.6096]]
+        if meta["case"].startswith("Sources"):
+            case = mg.SourceTerms(prm, geo, prod_points=pp + pp, inj_points=ip, heater_points=pp + ip)
+        else:
+            case = mg.WellHeaterCase(prm, geo, prod_points=pp, inj_points=ip)
+    m = Model(geo, case, prm, end=1.0, maxdt=1.0, small_dt_start=False, filename=mg.TMP, verbosity=False,
+              solver_parameters=mg.sp(25 if two else 15))
+    m.u.arr = np.asarray(z["u"]).reshape(m.u.arr.shape).copy()
+    m.u_.arr = np.asarray(z["u_old"]).reshape(m.u_.arr.shape).copy()
+    m.dt.assign(meta["dt"])
+    # the rebuilt model must BE the fixture's model: same residual
+    F = np.real(fd.assemble(m.F)).reshape(z["F"].shape)
+    assert np.abs(F - z["F"]).max() <= 1e-13 * np.abs(z["F"]).max(), name
+    appctx = dict(m.appctx)
+    appctx["state"] = m.u
+    pc = object.__new__(ref.ConvDiffSchurTwoPhasesPC if two else ref.ConvDiffSchurPC)
+    try:
+        pc.initialize(_FakePC(appctx))
+        raise RuntimeError("initialize() returned without assembling")
+    except Assembled:
+        pass
+    return pc.A.stencil
+
+
 def main():
     out = {}
+    for name in ("g2_sp2d_hetero_peaceman", "g3_tp2d_hetero_peaceman", "g4_sp3d_hetero_wellheater",
+                 "g5_tp3d_hetero_wellheater", "g6_tp3d_sources"):
+        A = convdiff(name)
+        out[name + "|convdiff|A"] = A
+        print("%-48s A_T %s  |diag|max %.3e  offdiag/diag max %.3f" % (name + "|convdiff", A.shape, np.abs(A[0]).max(),
+                                                                     (np.abs(A[1:]).sum(axis=0) / np.abs(A[0])).max()))
     for name, two_phase in (("g2_sp2d_hetero_peaceman", False), ("g3_tp2d_hetero_peaceman", True),
                             ("g5_tp3d_hetero_wellheater", True)):
         meta, pb, z = load(name)

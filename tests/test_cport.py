@@ -246,3 +246,38 @@ def test_decoupling_matches_the_references_own_algebra(key):
     assert repaired.sum() <= 0.05 * repaired.size
     assert rel_err_rows(A, expect) < 1e-11, key
     eng.close()
+
+
+def _pc_convdiff_cases():
+    import os
+    from tests.golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "pc", "decoup.npz"))
+    return sorted(k.split("|")[0] for k in z.files if k.endswith("|convdiff|A"))
+
+
+@pytest.mark.parametrize("name", _pc_convdiff_cases())
+def test_convdiff_operator_matches_the_references_own_form(name):
+    """The temperature Schur approximation against the operator the reference's ConvDiffSchurPC /
+    ConvDiffSchurTwoPhasesPC classes (preconditioners.py:11-118, 165-286) assemble from the same state: their
+    initialize() executed unmodified over the DG0 shim by tests/golden/make_pc_golden.py."""
+    import os
+    from tests.golden_util import GOLDEN_DIR
+    fix = np.load(os.path.join(GOLDEN_DIR, "pc", "decoup.npz"))
+    meta, pb, z = load(name)
+    eng = cport.engine_from_problem(pb)
+    if pb.nf == 2:
+        eng.set_solver_opts(stage1=cport.S1_FIELDSPLIT, schur_pre=cport.SCHUR_CONVDIFF, stage2=cport.S2_NONE, mg_dd_stop=0.0)
+    else:
+        eng.set_solver_opts(stage1=cport.S1_CPTR, decoup=0, schur_pre=cport.SCHUR_CONVDIFF, mg_dd_stop=0.0)
+    eng.pc_setup(np.ascontiguousarray(z["J"]), z["u"], meta["dt"])
+    A, A_ref = eng.mg_level_op(1, 0), fix[name + "|convdiff|A"]
+    # row repair of the multigrid's copy (see test_decoupling_matches_the_references_own_algebra): these fixtures'
+    # random states make the operator strongly convective, so a good share of the rows is repaired
+    off = np.abs(A_ref[1:]).sum(axis=0)
+    repaired = A_ref[0] < 0.8 * off
+    expect = A_ref.copy()
+    expect[0, repaired] = off[repaired]
+    assert rel_err_rows(A[1:], A_ref[1:]) < 1e-12, name
+    assert rel_err_rows(A, expect) < 1e-12, name
+    assert (~repaired).sum() >= 0.3 * repaired.size     # and a good share is compared as the reference made it
+    eng.close()
