@@ -125,10 +125,10 @@ class _FakePC:
         return None, None
 
 
-def convdiff(name):
-    """rebuild the reference model of a residual fixture and let the reference's PC class assemble its operator"""
+def rebuild(name):
+    """the reference model of a residual fixture, rebuilt from the fixture's own inputs (fields, parameters, state, dt)
+    with the well/heater set-ups of make_golden.py; checked to reproduce the fixture's residual"""
     import firedrake as fd
-    from firedrake.assemble import Assembled
     import make_golden as mg
     meta, pb, z = load(name)
     g = pb.grid
@@ -137,7 +137,10 @@ def convdiff(name):
     fields = tuple(np.asarray(z[k]).reshape(shape) if z[k].size else None for k in ("phi", "Kx", "Ky", "Kz"))
     two = meta["nphase"] == 2
     Model = mg.TwoPhase if two else mg.SinglePhase
-    if g.dim == 2:
+    if name.startswith("g1_"):
+        geo = mg.HomogeneousGeo(g.nx, g.ny, prm, g.nx * g.dx, g.ny * g.dy)
+        case = mg.WellCase(prm, geo, well_case="test0", constant_rate=True)
+    elif g.dim == 2:
         geo = mg.HeteroGeo2D(g.nx, g.ny, prm, fields, dx=g.dx, dy=g.dy)
         pts_p, pts_i = [[2.3 * 6.096, 4.6 * 3.048]], [[9.4 * 6.096, 7.2 * 3.048]]
         case = mg.WellCase(prm, geo, prod_points=pts_p, inj_points=pts_i)
@@ -154,9 +157,15 @@ def convdiff(name):
     m.u.arr = np.asarray(z["u"]).reshape(m.u.arr.shape).copy()
     m.u_.arr = np.asarray(z["u_old"]).reshape(m.u_.arr.shape).copy()
     m.dt.assign(meta["dt"])
-    # the rebuilt model must BE the fixture's model: same residual
     F = np.real(fd.assemble(m.F)).reshape(z["F"].shape)
     assert np.abs(F - z["F"]).max() <= 1e-13 * np.abs(z["F"]).max(), name
+    return m, case, two
+
+
+def convdiff(name):
+    """let the reference's PC class assemble its operator on the rebuilt model"""
+    from firedrake.assemble import Assembled
+    m, case, two = rebuild(name)
     appctx = dict(m.appctx)
     appctx["state"] = m.u
     pc = object.__new__(ref.ConvDiffSchurTwoPhasesPC if two else ref.ConvDiffSchurPC)
@@ -168,8 +177,36 @@ def convdiff(name):
     return pc.A.stencil
 
 
+def rates(name):
+    """the well totals of thermalmodel.py:231-270, from the rate expressions the reference's form code attached to its
+    wells (singlephase.py:151-162, twophase.py:362-408); order: injection, production, oil, water (NaN = not reported)"""
+    from firedrake import assemble, dx
+    m, case, two = rebuild(name)
+    out = [np.nan] * 4
+    if case.name.startswith("Sources"):
+        out[0] = assemble(case.deltas_inj * m.inj_rate * dx)
+        out[1] = assemble(case.deltas_prod * m.prod_rate * dx)
+        if two:
+            out[2] = assemble(case.deltas_prod * m.oil_rate * dx)
+            out[3] = assemble(case.deltas_prod * m.water_rate * dx)
+    if case.inj_wells:
+        out[0] = assemble(sum(w["delta"] * w["rate"] * dx for w in case.inj_wells))
+    if case.prod_wells:
+        out[1] = assemble(sum(w["delta"] * w["rate"] * dx for w in case.prod_wells))
+        if two:
+            out[3] = assemble(sum(w["delta"] * w["water_rate"] * dx for w in case.prod_wells))
+            out[2] = assemble(sum(w["delta"] * w["oil_rate"] * dx for w in case.prod_wells))
+    return np.array([float(np.real(v)) for v in out])
+
+
 def main():
     out = {}
+    for name in ("g1_sp2d_homo_const", "g2_sp2d_hetero_peaceman", "g3_tp2d_hetero_peaceman",
+                 "g3b_tp2d_hetero_peaceman_uncapped", "g4_sp3d_hetero_wellheater", "g5_tp3d_hetero_wellheater",
+                 "g5b_tp3d_hetero_wellheater_dp", "g6_tp3d_sources"):
+        r = rates(name)
+        out[name + "|rates|q"] = r
+        print("%-48s inj %.6e  prod %.6e  oil %.6e  water %.6e" % ((name + "|rates",) + tuple(r)))
     for name in ("g2_sp2d_hetero_peaceman", "g3_tp2d_hetero_peaceman", "g4_sp3d_hetero_wellheater",
                  "g5_tp3d_hetero_wellheater", "g6_tp3d_sources"):
         A = convdiff(name)

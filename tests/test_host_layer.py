@@ -237,3 +237,63 @@ def test_vti_pvd_output_and_matlab_dumps(tmp_path):
     assert A.shape == (3 * g.ncell, 3 * g.ncell) and np.abs(A @ x.reshape(-1) - y.reshape(-1)).max() < 1e-13
     V.export_residual(x, str(tmp_path / "rhs.txt"))
     assert np.array_equal(V.load_matlab_vector(str(tmp_path / "rhs.txt")), x.reshape(-1))
+
+
+def _rate_fixture_names():
+    import os
+    from tests.golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "pc", "decoup.npz"))
+    return sorted(k.split("|")[0] for k in z.files if k.endswith("|rates|q"))
+
+
+@pytest.mark.parametrize("name", _rate_fixture_names())
+def test_well_totals_match_the_reference_expressions(name):
+    """cases.source_rates (the per-step totals of thermalmodel.py:231-270) against the reference's own rate
+    expressions evaluated at the fixture states (tests/golden/make_pc_golden.py: rates)."""
+    import os
+    from tests.golden_util import GOLDEN_DIR
+    want = np.load(os.path.join(GOLDEN_DIR, "pc", "decoup.npz"))[name + "|rates|q"]
+    meta, pb, z = load(name)
+    prm = PhysicalParameters()
+    for k, v in meta["params"].items():
+        setattr(prm, k, v)
+    ent = [(s.cell, s.kind, s.weight, s.bhp, s.max_rate, s.const_rate) for s in pb.sources]
+    cells = np.array([e[0] for e in ent])
+    got = CS.source_rates(ent, z["u"][:, cells], pb.Kx[cells], pb.Ky[cells], prm, pb.nphase)
+    for key, ref in zip(("inj", "prod", "oil", "water"), want):
+        if np.isnan(ref):
+            assert got.get(key) is None
+        else:
+            assert got[key] == pytest.approx(ref, rel=1e-12, abs=0.0), (name, key)
+
+
+def test_model_reports_the_well_totals_in_the_reference_order():
+    """ThermalModel.well_totals gathers the state at the source cells (here on a CPU tensor standing in for the
+    device state) and rate_lines prints what thermalmodel.py:231-270 prints, in its order."""
+    import os
+    import torch
+    from tests.golden_util import GOLDEN_DIR
+    from thermalporous_b200.model import ThermalModel, rate_lines
+    name = "g5_tp3d_hetero_wellheater"
+    want = np.load(os.path.join(GOLDEN_DIR, "pc", "decoup.npz"))[name + "|rates|q"]
+    meta, pb, z = load(name)
+    prm = PhysicalParameters()
+    for k, v in meta["params"].items():
+        setattr(prm, k, v)
+
+    class Fake:
+        pass
+    m = Fake()
+    m._entries = [(s.cell, s.kind, s.weight, s.bhp, s.max_rate, s.const_rate) for s in pb.sources]
+    cells = np.array([e[0] for e in m._entries])
+    m._src_K = (pb.Kx[cells], pb.Ky[cells])
+    m.u = torch.from_numpy(np.ascontiguousarray(z["u"]))
+    m.params, m.nphase, m.world = prm, 2, 1
+    tot = ThermalModel.well_totals(m)
+    for key, ref in zip(("inj", "prod", "oil", "water"), want):
+        assert tot[key] == pytest.approx(ref, rel=1e-12)
+    lines = rate_lines(tot, sources_case=False)
+    assert [ln.split(" is ")[0] for ln in lines] == ["Total injection rate", "Total water production rate",
+                                                     "Total oil production rate", "Total production rate"]
+    lines = rate_lines({"inj": 1.0, "prod": -1.0, "oil": None, "water": None}, sources_case=True)
+    assert lines == ["Total injection rate is 1.0", "Total production rate is -1.0"]

@@ -292,3 +292,57 @@ def source_entries(case, params, geo):
     for h in getattr(case, "heaters", []) or []:
         add(h["delta"], HEATER, 0.0, 0.0)
     return out
+
+
+def source_rates(entries, u_at, Kx_at, Ky_at, params, nphase):
+    """The volumetric well totals the reference's time loop evaluates after every step (thermalmodel.py:231-270:
+    `assemble(delta * rate * dx)` summed over the wells, or over the global deltas of a SourceTerms case).
+
+    entries: records as returned by source_entries() (cell, kind, weight = delta * cell volume, bhp, max_rate,
+    const_rate); u_at[f][e], Kx_at[e], Ky_at[e]: state and horizontal permeabilities at each record's cell.
+    The rate laws are wellcase.py:171-266 / sourceterms.py:155-269 (Peaceman index with h = 5, rw = 0.1, Dx = Dy = 5
+    hard-wired; the side of the draw-down conditional follows the sign of max_rate; rates at or beyond max_rate are
+    capped; oil viscosity for every single-phase well, mixture mobility for two-phase producers, water for two-phase
+    injectors; twophase.py:388-408, singlephase.py:151-162).  Returns {"inj", "prod"[, "oil", "water"]} with None for
+    an absent well type; heaters carry no rate."""
+    out = {"inj": None, "prod": None}
+    if nphase == 2:
+        out.update(oil=None, water=None)
+    ent = [(k, e) for k, e in enumerate(entries) if e[1] in (PROD, INJ)]
+    if not ent:
+        return out
+    idx = np.array([k for k, _ in ent])
+    kind = np.array([e[1] for _, e in ent])
+    w = np.array([e[2] for _, e in ent], dtype=float)
+    bhp = np.array([e[3] for _, e in ent], dtype=float)
+    qmax = np.array([e[4] for _, e in ent], dtype=float)
+    const = np.array([bool(e[5]) for _, e in ent])
+    u_at = np.asarray(u_at, dtype=float)
+    p, T = u_at[0][idx], u_at[1][idx]
+    imu_o = 1.0 / params.oil_mu(T)
+    if nphase == 2:
+        S = u_at[2][idx]
+        imu_w = 1.0 / params.water_mu(T)
+        mu_mix = 1.0 / (S * imu_o + (1.0 - S) * imu_w)                   # wellcase.py:212
+        mu = np.where(kind == PROD, mu_mix, 1.0 / imu_w)                 # injectors: phase='water' (twophase.py:401)
+    else:
+        mu = 1.0 / imu_o
+    Kx, Ky = np.asarray(Kx_at, dtype=float)[idx], np.asarray(Ky_at, dtype=float)[idx]
+    h, rw, Dx, Dy = 5.0, 0.1, 5.0, 5.0                                   # wellcase.py:182-189
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ro = 0.28 * ((Ky / Kx) ** 0.5 * Dx ** 2 + (Kx / Ky) ** 0.5 * Dy ** 2) ** 0.5 / ((Ky / Kx) ** 0.25 + (Kx / Ky) ** 0.25)
+        factor = 2.0 * np.pi * h * (Kx * Ky) ** 0.5 / np.log(ro / rw) / mu
+    d = bhp - p
+    dd = np.where(qmax < 0.0, np.where(d >= 0.0, 0.0, d), np.where(d <= 0.0, 0.0, d))   # :193-196
+    rate = factor * dd
+    rate = np.where(np.abs(rate) - np.abs(qmax) >= 0.0, qmax, rate)     # :198
+    rate = np.where(const, qmax, rate)                                   # flow_rate_constant (:200-201, 236-266)
+    for name, k in (("inj", INJ), ("prod", PROD)):
+        m = kind == k
+        if m.any():
+            out[name] = float(np.sum(w[m] * rate[m]))
+    if nphase == 2 and (kind == PROD).any():
+        m = kind == PROD
+        out["water"] = float(np.sum(w[m] * ((1.0 - S[m]) * imu_w[m] * mu[m] * rate[m])))   # :233
+        out["oil"] = float(np.sum(w[m] * (S[m] * imu_o[m] * mu[m] * rate[m])))             # :234
+    return out

@@ -17,7 +17,7 @@ import time
 import numpy as np
 
 from . import options as O
-from .cases import source_entries
+from .cases import source_entries, source_rates
 
 DAY = 24.0 * 3600.0
 
@@ -135,6 +135,15 @@ def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_
     return res
 
 
+def rate_lines(rates, sources_case):
+    """the lines thermalmodel.py:231-270 prints after a step, in its order: a SourceTerms case reports injection,
+    production, oil, water; a case with individual wells injection, then water, oil and total production"""
+    fmt = {"inj": "Total injection rate is ", "prod": "Total production rate is ",
+           "oil": "Total oil production rate is ", "water": "Total water production rate is "}
+    order = ("inj", "prod", "oil", "water") if sources_case else ("inj", "water", "oil", "prod")
+    return [fmt[k] + repr(rates[k]) for k in order if rates.get(k) is not None]
+
+
 def save_checkpoint(name, u):
     """store the solution fields (nf, ncell) - stands in for DumbCheckpoint.store (thermalmodel.py:361-364)."""
     np.savez(name if name.endswith(".npz") else name + ".npz", solution=np.asarray(u))
@@ -203,7 +212,10 @@ class ThermalModel:
             e.set_field(L.TPB_KZ, slab.take(geo.K_z))
         if self.nphase == 1:
             e.set_field(L.TPB_KT, slab.take(geo.kT))
-        e.set_sources(slab.localize_sources(source_entries(self.case, prm, geo)))
+        self._entries = slab.localize_sources(source_entries(self.case, prm, geo))
+        e.set_sources(self._entries)
+        src_cells = np.array([s[0] for s in self._entries], dtype=np.int64)
+        self._src_K = (slab.take(geo.K_x)[src_cells], slab.take(geo.K_y)[src_cells])   # for well_totals()
         if self.world > 1:
             import torch.distributed as dist
             uid = [e.unique_id() if self.rank == 0 else None]
@@ -246,6 +258,9 @@ class ThermalModel:
         state = {"i_plot": 0}
 
         def after_step(t):
+            if self.verbosity:                                           # thermalmodel.py:231-270
+                for line in rate_lines(self.well_totals(), self.case.name.startswith("Sources")):
+                    self.resultprint(line)
             if writer is not None:                                       # thermalmodel.py:304-320
                 if state["i_plot"] % self.n_save == 0:
                     writer.write(t, self.fields())
@@ -281,6 +296,26 @@ class ThermalModel:
             p("Average Linear iteration per Nonlinear iteration: ", res.total_lits / max(res.total_nits, 1))
             p("Number of time-steps: ", n)
         return res
+
+    def well_totals(self):
+        """volumetric injection / production (/ oil / water) totals at the current state, over all ranks' slabs
+        (thermalmodel.py:231-270; cases.source_rates).  Reads the state at the source cells only."""
+        import torch
+        ent = self._entries
+        keys = ("inj", "prod") + (("oil", "water") if self.nphase == 2 else ())
+        if ent:
+            cells = np.array([e[0] for e in ent], dtype=np.int64)
+            at = self.u[:, torch.as_tensor(cells, device=self.u.device)].detach().cpu().numpy()
+            tot = source_rates(ent, at, self._src_K[0], self._src_K[1], self.params, self.nphase)
+        else:
+            tot = dict.fromkeys(keys)
+        if self.world > 1:
+            import torch.distributed as dist
+            v = torch.tensor([[0.0 if tot[k] is None else tot[k], 0.0 if tot[k] is None else 1.0] for k in keys],
+                             device=self.u.device, dtype=torch.float64)
+            dist.all_reduce(v)
+            tot = {k: (float(v[i, 0]) if float(v[i, 1]) > 0 else None) for i, k in enumerate(keys)}
+        return tot
 
     def fields(self):
         """converged fields of THIS rank's slab as host arrays: (p, T[, S_o]); cells self.slab.c0 .. c1 of the geo."""
