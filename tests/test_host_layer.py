@@ -1,4 +1,5 @@
 """Host-side mirror of the reference's geo / case / option surface (no GPU needed)."""
+import os
 import numpy as np
 import pytest
 
@@ -297,3 +298,23 @@ def test_model_reports_the_well_totals_in_the_reference_order():
                                                      "Total oil production rate", "Total production rate"]
     lines = rate_lines({"inj": 1.0, "prod": -1.0, "oil": None, "water": None}, sources_case=True)
     assert lines == ["Total injection rate is 1.0", "Total production rate is -1.0"]
+
+
+def test_results_file_follows_the_reference(tmp_path):
+    """thermalmodel.py:28-32,78-80: resultprint goes to the screen and to the results file; nothing is written by a
+    quiet model."""
+    from thermalporous_b200.model import ThermalModel
+
+    class Fake:
+        pass
+    for verbosity, expect in ((True, True), (False, False)):
+        m = Fake()
+        m.verbosity, m.rank = verbosity, 0
+        m.filename, m._results_file = str(tmp_path / ("r%d" % verbosity) / "results.txt"), None
+        ThermalModel.resultprint(m, "nits = ", [4, 5], ";")
+        ThermalModel.resultprint(m, "Total Linear iterations: ", 9)
+        if m._results_file is not None:
+            m._results_file.close()
+        assert os.path.exists(m.filename) == expect
+        if expect:
+            assert open(m.filename).read() == "nits =  [4, 5] ;\nTotal Linear iterations:  9\n"

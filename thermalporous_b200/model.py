@@ -12,6 +12,7 @@ on the CPU (tests/) without a device; the models below always bind it to the CUD
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -188,6 +189,7 @@ class ThermalModel:
         self.checkpointing.update(checkpointing or {})
         self.maxdt, self.dt_init_fact, self.end, self.verbosity = maxdt, dt_init_fact, end, verbosity
         self.filename = filename
+        self._results_file = None
         geo, prm = self.geo, self.params
         # One process per GPU: under `torchrun` (torch.distributed initialised with the nccl backend) every rank
         # owns one z-slab (y-slab in 2-D) of the geo, as every MPI rank owns a mesh partition in the reference
@@ -235,8 +237,19 @@ class ThermalModel:
         self.result = None
 
     def resultprint(self, *args):
-        if self.verbosity and self.rank == 0:
-            print(*args)
+        """thermalmodel.py:78-80: to the screen and to the results file (appended to when it is the default
+        results/results.txt, overwritten otherwise, :28-32).  Rank 0 only; the file is opened on first use, so a
+        quiet model (verbosity=False) never touches the file system."""
+        if not (self.verbosity and self.rank == 0):
+            return
+        print(*args)
+        if self._results_file is None:
+            d = os.path.dirname(self.filename)
+            if d:
+                os.makedirs(d, exist_ok=True)
+            self._results_file = open(self.filename, "a" if self.filename == "results/results.txt" else "w")
+        print(*args, file=self._results_file)
+        self._results_file.flush()
 
     def _rank_suffix(self):
         return "" if self.world == 1 else "_rank%dof%d" % (self.rank, self.world)
@@ -285,16 +298,36 @@ class ThermalModel:
             p("lits = ", res.lits_vec, ";")
             p("dts = ", res.dt_vec, ";")
             p("timings = ", res.timings, ";")
+            p("----------------------------------------------------------------------")
             p(self.name, "thermal model")
             p("Geo model: ", self.geo.name)
             p("Test case: ", self.case.name)
-            p("Solver: ", self.solver_desc)
+            p("Max time-step: ", self.maxdt)
+            p("Final time: ", res.t / DAY)
+            p("Solver Parameters")
+            p("-----------------")
+            sp = self.solver_parameters
+            if isinstance(sp, dict):
+                for x in sp:
+                    p(x, ":", sp[x])
+            p("realised as: ", self.solver_desc)
+            if self.nphase == 1 and self.solver_opts.get("stage1") == O.S1_FIELDSPLIT:
+                p("pressure-temperature ordering for fieldsplit")          # singlephase.py:283
+            p(" ")
+            p("Solver performance")
+            p("------------------")
             p("Total CPU time (s):", sum(res.timings))
             n = len(res.dt_vec)
             p("Average Nonlinear iterations per time-step:", res.total_nits / n)
             p("Average Linear iterations per time-step: ", res.total_lits / n)
             p("Average Linear iteration per Nonlinear iteration: ", res.total_lits / max(res.total_nits, 1))
+            p("Total Linear iterations: ", res.total_lits)
+            p("Total Nonlinear iterations: ", res.total_nits)
             p("Number of time-steps: ", n)
+            p("Last Nonlinear iterations:", res.nits_vec[-1])
+            p("Last Linear iterations: ", res.lits_vec[-1])
+            p("----------------------------------------------------------------------")
+            p(" ")
         return res
 
     def well_totals(self):
