@@ -56,8 +56,27 @@ def _worker(rank, world, port, q):
     from bench import NpOps
     sat = np.stack([np.zeros(slab.ncell), np.zeros(slab.ncell), np.linspace(0.2 + rank, 0.5 + rank, slab.ncell)])
     smin, smax = NpOps(dist, None).minmax(sat, 2)
+    # the per-step well totals (thermalmodel.py:231-270) are sums over every rank's source cells
+    from thermalporous_b200.model import ThermalModel
+
+    class _M:
+        pass
+    rng = np.random.default_rng(11)
+    ug = np.stack([prm.p_ref + rng.uniform(-0.5, 0.5, geo.ncell), rng.uniform(290.0, 330.0, geo.ncell),
+                   rng.uniform(0.3, 0.9, geo.ncell)])
+
+    def totals(entries, u, kx, ky, world_):
+        m = _M()
+        m._entries, m.u, m.params, m.nphase, m.world = entries, torch.from_numpy(np.ascontiguousarray(u)), prm, 2, world_
+        cells = np.array([e_[0] for e_ in entries], dtype=np.int64)
+        m._src_K = (kx[cells], ky[cells])
+        return ThermalModel.well_totals(m)
+    t_loc = totals(loc, slab.take(ug), slab.take(geo.K_x), slab.take(geo.K_y), world)
+    t_glob = totals(ent, ug, geo.K_x, geo.K_y, 1)
+    tot_ok = all((t_glob[k] is None and t_loc[k] is None) or abs(t_loc[k] - t_glob[k]) <= 1e-12 * abs(t_glob[k])
+                 for k in t_glob)
     ok = (cnt.item() == len(ent) and np.array_equal(np.concatenate(pieces), geo.K_z) and uid[0] == bytes(range(128))
-          and abs(smin - 0.2) < 1e-15 and abs(smax - 1.5) < 1e-15
+          and abs(smin - 0.2) < 1e-15 and abs(smax - 1.5) < 1e-15 and tot_ok and t_glob["prod"] is not None
           and slab.local_dims() == (6, 8, 5) and slab.has_lo == (rank == 1) and slab.has_hi == (rank == 0)
           and all(0 <= e[0] < slab.ncell for e in loc)
           and (rank == 0 or np.array_equal(lo.numpy(), geo.phi[slab.c0 - slab.np:slab.c0])))
