@@ -318,3 +318,29 @@ def test_results_file_follows_the_reference(tmp_path):
         assert os.path.exists(m.filename) == expect
         if expect:
             assert open(m.filename).read() == "nits =  [4, 5] ;\nTotal Linear iterations:  9\n"
+
+
+def test_named_option_sets_equal_the_references_own_dictionaries():
+    """options.resolve(name) against options.resolve(<the dict the reference's init_solver_parameters builds for that
+    name>) - the dictionaries come from the reference's own dispatchers (tests/golden/make_option_golden.py).
+    One deliberate difference: every two-phase set of the reference starts from `newton_fas_krylov` (twophase.py:434-
+    518, 927), whose FAS nonlinear preconditioner needs a mesh hierarchy and whose l2 line search belongs to it; the
+    named sets here keep the Newton-Krylov part with the basic line search (out of scope), while a raw
+    dict's snes_linesearch_type is honoured."""
+    import json
+    from tests.golden_util import GOLDEN_DIR
+    sets = json.load(open(os.path.join(GOLDEN_DIR, "pc", "option_sets.json")))
+    assert len(sets) == len(O.SINGLE_PHASE_SETS) + len(O.TWO_PHASE_SETS) + 2
+    for key, rec in sets.items():
+        nphase, name = key.split("|")
+        nphase, name = int(nphase), (None if name == "None" else name)
+        d = dict(rec["parameters"])
+        if rec["decoup"] != "No":
+            d["sub_0_cpr_decoup"] = rec["decoup"]
+        by_name, dec_name, _ = O.resolve(name, nphase)
+        by_dict, dec_dict, _ = O.resolve(d, nphase)
+        assert dec_name == dec_dict == rec["decoup"], key
+        if nphase == 2:
+            assert d.get("snes_linesearch_type") == "l2" and by_dict.pop("linesearch") == 1
+            assert "linesearch" not in by_name
+        assert by_name == by_dict, key
