@@ -119,10 +119,22 @@ typedef struct {
                                  most mg_coarse_sweeps) instead of being coarsened - what BoomerAMG's max_row_sum does
                                  to diagonally dominant rows.  The temperature Schur block is such a matrix while dt
                                  is small.  0 = never */
+    double mg_coarse_scale;   /* Galerkin coarse operators of piecewise-constant aggregates are too stiff by a factor 2
+                                 along every coarsened axis (the cell-centred multigrid scaling defect: the coarse
+                                 centres are 2h apart, the summed face couplings still act over h): the couplings
+                                 along a coarsened axis are multiplied by this factor, row sums are kept.  0.5 = the
+                                 exact factor for smooth coefficients (default); 1 = plain Galerkin */
+    int mg_smoother;          /* tpb_mg_smoother: 0 red-black point Gauss-Seidel, 1 zebra z-line Gauss-Seidel (3-D:
+                                 columns coloured by (i+j)&1, every column solved exactly by the Thomas algorithm; z is
+                                 then never coarsened while x or y can be) - what thin reservoir layers (Dz << Dx, Dy)
+                                 need.  Default 1 in 3-D; 2-D grids always use 0 */
     /* second stage: block ILU(0) of the nf x nf block stencil in red-black ordering, one block per
-     * rank as PETSc bjacobi+ilu (the slab couplings to other ranks are dropped) */
+     * rank as PETSc bjacobi+ilu (the slab couplings to other ranks are dropped).  The triangular solves read an
+     * fp32 colour-separated copy of the factor (fp64 arithmetic): a fixed preconditioner, converged fields are
+     * unaffected */
     int verbose;
 } tpb_solver_opts;
+enum tpb_mg_smoother { TPB_MG_RBGS = 0, TPB_MG_ZLINE = 1 };
 
 typedef struct {
     int nits;                 /* snes.getIterationNumber(), thermalmodel.py:327 */

@@ -60,6 +60,8 @@ typedef struct {
     int cx, cy, cz; /* coarsening factors towards the next level */
     double* a;
     double *x, *b, *r;
+    int line;            /* smoothed by zebra z-line Gauss-Seidel (tpb_solver_opts.mg_smoother) */
+    double *lid, *llf, *lcp; /* Thomas factors of every column: 1/pivot, lower * 1/pivot, upper * 1/pivot */
 } mglevel;
 
 typedef struct {
@@ -550,12 +552,16 @@ static void mg_free(mghier* m) {
         free(m->lev[l].x);
         free(m->lev[l].b);
         free(m->lev[l].r);
+        free(m->lev[l].lid);
+        free(m->lev[l].llf);
+        free(m->lev[l].lcp);
+        m->lev[l].lid = m->lev[l].llf = m->lev[l].lcp = NULL;
     }
     m->nlev = 0;
 }
 
 /* Galerkin coarse operator for piecewise-constant aggregation: stays a 5|7-point stencil */
-static void mg_coarsen_op(const mglevel* f, mglevel* c, int ns) {
+static void mg_coarsen_op(const mglevel* f, mglevel* c, int ns, double sc) {
     const int cx = f->cx, cy = f->cy, cz = f->cz;
     memset(c->a, 0, sizeof(double) * ns * c->n);
 #pragma omp parallel for schedule(static)
@@ -578,7 +584,43 @@ static void mg_coarsen_op(const mglevel* f, mglevel* c, int ns) {
                         acc[same ? 0 : s] += f->a[(long)s * f->n + fc];
                     }
                 }
+        /* tpb_solver_opts.mg_coarse_scale: couplings along a coarsened axis are scaled, row sums kept */
+        if (sc != 1.0)
+            for (int s = 1; s < ns; s++) {
+                int axis = (s - 1) >> 1;
+                int cf = axis == 0 ? cx : (axis == 1 ? cy : cz);
+                if (cf == 2) {
+                    double nv = sc * acc[s];
+                    acc[0] += acc[s] - nv;
+                    acc[s] = nv;
+                }
+            }
         for (int s = 0; s < ns; s++) c->a[(long)s * c->n + C] = acc[s];
+    }
+}
+
+/* LU factors of every column's tridiagonal (diag, z-, z+): id = 1/pivot, lf = lower * id, cp = upper * id; the
+ * couplings through the bottom and the top of the box (k = 0 lower, k = nz-1 upper: slab faces on multi-rank runs)
+ * are not part of the column.  A zero pivot gives id = 0 (the row's x stays 0, as the point smoother does). */
+static void mg_line_factors(mglevel* L) {
+    const int nz = L->nz;
+    const long n = L->n, np = (long)L->nx * L->ny;
+    L->lid = (double*)malloc(sizeof(double) * n);
+    L->llf = (double*)malloc(sizeof(double) * n);
+    L->lcp = (double*)malloc(sizeof(double) * n);
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < np; q++) {
+        double cprev = 0.0;
+        for (int k = 0; k < nz; k++) {
+            long c = q + np * k;
+            double lo = k > 0 ? L->a[5 * n + c] : 0.0, up = k < nz - 1 ? L->a[6 * n + c] : 0.0;
+            double den = L->a[c] - lo * cprev;
+            double id = den != 0.0 ? 1.0 / den : 0.0;
+            L->lid[c] = id;
+            L->llf[c] = lo * id;
+            cprev = up * id;
+            L->lcp[c] = cprev;
+        }
     }
 }
 
@@ -605,6 +647,8 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
     L->n = h->g.n;
     L->a = a0;
     m->last_sweeps = 0;
+    /* zebra z-line smoothing (tpb_solver_opts.mg_smoother) on every level of a 3-D hierarchy; z is then not coarsened */
+    const int line = (o->mg_smoother == TPB_MG_ZLINE && ns == 7 && h->g.nz > 1);
     int l = 0;
     for (;;) {
         L = &m->lev[l];
@@ -612,6 +656,13 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
         L->b = (double*)calloc(L->n, sizeof(double));
         L->r = (double*)calloc(L->n, sizeof(double));
         L->cx = L->cy = L->cz = 1;
+        L->line = line;
+        L->lid = L->llf = L->lcp = NULL;
+        if (line) mg_line_factors(L);
+        if (line && L->nx == 1 && L->ny == 1) { /* a single column: the line solve is exact */
+            m->last_sweeps = 1;
+            break;
+        }
         if (L->n <= o->mg_min_cells || L->n <= 1 || l == MAXLEV - 1) break;
         if (o->mg_dd_stop > 0.0) {
             /* strongest row of the level: max over cells of sum|off-diag| / |diag| */
@@ -640,6 +691,7 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
             for (long c = 0; c < L->n; c++) sum += fabs(a1[c]) + fabs(a2[c]);
             m_ax[ax] = sum;
         }
+        if (line) dims[2] = 1; /* z-line smoothing: z is never coarsened */
         double mmax = 0.0;
         for (int ax = 0; ax < 3; ax++)
             if (dims[ax] > 1 && m_ax[ax] > mmax) mmax = m_ax[ax];
@@ -663,7 +715,7 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
         Cc->nz = (L->nz + cf[2] - 1) / cf[2];
         Cc->n = (long)Cc->nx * Cc->ny * Cc->nz;
         Cc->a = (double*)malloc(sizeof(double) * ns * Cc->n);
-        mg_coarsen_op(L, Cc, ns);
+        mg_coarsen_op(L, Cc, ns, o->mg_coarse_scale > 0.0 ? o->mg_coarse_scale : 1.0);
         l++;
     }
     m->nlev = l + 1;
@@ -692,6 +744,48 @@ static void mg_rbgs(const mglevel* L, int ns, const double* b, double* x, int ze
     }
 }
 
+/* zebra z-line Gauss-Seidel: columns coloured by (i+j)&1, every column of a colour solved exactly by the Thomas
+ * algorithm with the factors of mg_line_factors (same arithmetic as csrc/tpb_pc.cu zline kernels):
+ *   d_k = rhs_k * id_k - lf_k * d_{k-1} ;  x_k = d_k - cp_k * x_{k+1}
+ * rhs_k = b_k - sum over the four lateral neighbours (x-, x+, y-, y+; the other colour) */
+static void mg_zline(const mglevel* L, const double* b, double* x, int zero_guess) {
+    const int nx = L->nx, ny = L->ny, nz = L->nz;
+    const long n = L->n, np = (long)nx * ny;
+    for (int col = 0; col < 2; col++) {
+#pragma omp parallel for schedule(static)
+        for (long q = 0; q < np; q++) {
+            int i = (int)(q % nx), j = (int)(q / nx);
+            if (((i + j) & 1) != col) continue;
+            double dprev = 0.0;
+            for (int k = 0; k < nz; k++) {
+                long c = q + np * k;
+                double rhs = b[c];
+                if (!(zero_guess && col == 0)) {
+                    for (int s = 1; s < 5; s++) {
+                        long nb = nbr(nx, ny, nz, i, j, k, s);
+                        if (nb >= 0) rhs -= L->a[(long)s * n + c] * x[nb];
+                    }
+                }
+                dprev = rhs * L->lid[c] - L->llf[c] * dprev;
+                x[c] = dprev;
+            }
+            double xn = 0.0;
+            for (int k = nz - 1; k >= 0; k--) {
+                long c = q + np * k;
+                xn = x[c] - L->lcp[c] * xn;
+                x[c] = xn;
+            }
+        }
+    }
+}
+
+static void mg_smooth(const mglevel* L, int ns, const double* b, double* x, int zero_guess) {
+    if (L->line)
+        mg_zline(L, b, x, zero_guess);
+    else
+        mg_rbgs(L, ns, b, x, zero_guess);
+}
+
 static void mg_residual(const mglevel* L, int ns, const double* b, const double* x, double* r) {
     const int nx = L->nx, ny = L->ny, nz = L->nz;
     const long n = L->n;
@@ -717,9 +811,10 @@ static void mg_restrict(const mglevel* f, const mglevel* c, const double* r, dou
                 for (int di = 0; di < f->cx; di++) {
                     int i = I * f->cx + di, j = Jc * f->cy + dj, k = Kc * f->cz + dk;
                     if (i >= f->nx || j >= f->ny || k >= f->nz) continue;
-                    /* the pre-smoothing sweep ended on colour 1: those rows were just solved, their residual is
-                     * zero and is not summed (csrc/tpb_pc.cu restrict_cell) */
-                    if ((i + j + k) & 1) continue;
+                    /* the pre-smoothing sweep ended on colour 1 (cells (i+j+k)&1, or columns (i+j)&1 of a line-smoothed
+                     * level): those rows were just solved, their residual is zero and is not summed
+                     * (csrc/tpb_pc.cu restrict_cell) */
+                    if (f->line ? ((i + j) & 1) : ((i + j + k) & 1)) continue;
                     acc += r[i + (long)f->nx * (j + (long)f->ny * k)];
                 }
         bc[C] = acc;
@@ -741,17 +836,17 @@ static void mg_vcycle_level(const tpc_handle_s* h, mghier* m, int l) {
     mglevel* L = &m->lev[l];
     if (l == m->nlev - 1) {
         int sweeps = m->last_sweeps > 0 ? m->last_sweeps : (o->mg_coarse_sweeps > 0 ? o->mg_coarse_sweeps : 1);
-        for (int s = 0; s < sweeps; s++) mg_rbgs(L, ns, L->b, L->x, s == 0);
+        for (int s = 0; s < sweeps; s++) mg_smooth(L, ns, L->b, L->x, s == 0);
         return;
     }
     int pre = o->mg_pre > 0 ? o->mg_pre : 1;
-    for (int s = 0; s < pre; s++) mg_rbgs(L, ns, L->b, L->x, s == 0);
+    for (int s = 0; s < pre; s++) mg_smooth(L, ns, L->b, L->x, s == 0);
     mg_residual(L, ns, L->b, L->x, L->r);
     mglevel* Cc = &m->lev[l + 1];
     mg_restrict(L, Cc, L->r, Cc->b);
     mg_vcycle_level(h, m, l + 1);
     mg_prolong_add(L, Cc, Cc->x, L->x, o->mg_overcorrection);
-    for (int s = 0; s < o->mg_post; s++) mg_rbgs(L, ns, L->b, L->x, 0);
+    for (int s = 0; s < o->mg_post; s++) mg_smooth(L, ns, L->b, L->x, 0);
 }
 
 /* y = V(b): mg_cycles V-cycles from a zero initial guess */

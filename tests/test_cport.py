@@ -80,15 +80,22 @@ def test_diagonally_dominant_levels_end_the_hierarchy():
         assert np.abs(on[4][f] - off[4][f]).max() <= 1e-8 * np.abs(off[4][f]).max()
 
 
-def test_galerkin_coarse_operators_preserve_row_sums():
-    """piecewise-constant Galerkin: the sum of all entries of a level equals that of the level above."""
+@pytest.mark.parametrize("smoother,scale", [(0, 1.0), (0, 0.5), (1, 0.5)])
+def test_galerkin_coarse_operators_preserve_row_sums(smoother, scale):
+    """piecewise-constant Galerkin: the sum of all entries of a level equals that of the level above - also with the
+    couplings along coarsened axes scaled (mg_coarse_scale moves what it takes off a coupling into the diagonal).
+    Point smoothing coarsens down to mg_min_cells; z-line smoothing never coarsens z and ends on a single column."""
     pb, u, uo = random_problem(3, 2, (9, 10, 11), seed=3, spread=0.05)
     eng = cport.engine_from_problem(pb)
-    eng.set_solver_opts(stage1=cport.S1_CPR, decoup=0)
+    eng.set_solver_opts(stage1=cport.S1_CPR, decoup=0, mg_smoother=smoother, mg_coarse_scale=scale)
     F, J = eng.assemble(u, uo, 4000.0)
     eng.pc_setup(J, u, 4000.0)
     lev = eng.mg_levels(0)
-    assert lev[0][:3] == (11, 10, 9) and lev[-1][0] * lev[-1][1] * lev[-1][2] <= 8
+    assert lev[0][:3] == (11, 10, 9)
+    if smoother == 0:
+        assert lev[-1][0] * lev[-1][1] * lev[-1][2] <= 8
+    else:
+        assert lev[-1][:3] == (1, 1, 9) and all(l[5] == 1 for l in lev)
     assert np.array_equal(eng.mg_level_op(0, 0), J[:, 0, 0, :])
     tot = [eng.mg_level_op(0, l).sum() for l in range(len(lev))]
     scale = np.abs(eng.mg_level_op(0, 0)).sum()

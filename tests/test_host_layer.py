@@ -325,22 +325,34 @@ def test_named_option_sets_equal_the_references_own_dictionaries():
     name>) - the dictionaries come from the reference's own dispatchers (tests/golden/make_option_golden.py).
     One deliberate difference: every two-phase set of the reference starts from `newton_fas_krylov` (twophase.py:434-
     518, 927), whose FAS nonlinear preconditioner needs a mesh hierarchy and whose l2 line search belongs to it; the
-    named sets here keep the Newton-Krylov part with the basic line search (out of scope), while a raw
-    dict's snes_linesearch_type is honoured."""
+    named sets here keep the Newton-Krylov part with the basic line search (out of scope); a raw dict that
+    asks for l2 is refused (no silent mapping onto another search).  The ILU(1) sets (pc_bilu, pc_cprilu1_gmres:
+    sub_pc_factor_levels 1) are refused by name and by dictionary: the second stage here is ILU(0)."""
     import json
     from tests.golden_util import GOLDEN_DIR
     sets = json.load(open(os.path.join(GOLDEN_DIR, "pc", "option_sets.json")))
-    assert len(sets) == len(O.SINGLE_PHASE_SETS) + len(O.TWO_PHASE_SETS) + 2
+    ilu1 = {"1|pc_ilu", "1|pc_bilu", "2|pc_bilu", "2|pc_cprilu1_gmres"}
+    assert len(sets) == len(O.SINGLE_PHASE_SETS) + len(O.TWO_PHASE_SETS) + 2 + len(ilu1)
     for key, rec in sets.items():
         nphase, name = key.split("|")
         nphase, name = int(nphase), (None if name == "None" else name)
         d = dict(rec["parameters"])
         if rec["decoup"] != "No":
             d["sub_0_cpr_decoup"] = rec["decoup"]
+        if nphase == 2:
+            with pytest.raises(O.UnsupportedOption):
+                O.resolve(dict(d), nphase)                         # l2 line search of the FAS branch
+            assert d.pop("snes_linesearch_type") == "l2"
+        if key in ilu1:
+            with pytest.raises(O.UnsupportedOption):
+                O.resolve(name, nphase)
+            with pytest.raises(O.UnsupportedOption):
+                O.resolve(d, nphase)
+            continue
         by_name, dec_name, _ = O.resolve(name, nphase)
         by_dict, dec_dict, _ = O.resolve(d, nphase)
         assert dec_name == dec_dict == rec["decoup"], key
-        if nphase == 2:
-            assert d.get("snes_linesearch_type") == "l2" and by_dict.pop("linesearch") == 1
-            assert "linesearch" not in by_name
+        assert "linesearch" not in by_name and "linesearch" not in by_dict
         assert by_name == by_dict, key
+    with pytest.raises(O.UnsupportedOption):
+        O.resolve({"pc_type": "ilu", "ksp_rtoll": 1e-5}, 1)        # a typo is an error, not a dropped key

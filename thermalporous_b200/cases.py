@@ -151,14 +151,17 @@ class HeaterCase(_CaseBase):
         heater_points = list(heater_points)
         if well_case is not None:
             # heatercase.py:18-51: the well presets, heaters at producers + injectors
-            table = dict(_PRESETS_2D) if geo.dim == 2 else dict(_PRESETS_3D)
-            if geo.dim == 3:
-                table["multiple"] = lambda s: (
+            # exactly the names heatercase.py handles: 2-D SPE10_60x120 / test0 / test ("default" sets only the unused
+            # prod/inj points there), 3-D default / multiple; any other name leaves heater_points untouched
+            if geo.dim == 2:
+                table = {k: _PRESETS_2D[k] for k in ("SPE10_60x120", "test0", "test")}
+            else:
+                table = {"default": _PRESETS_3D["default"], "multiple": lambda s: (
                     [[s.Length / 4, s.Length_y / 2, s.Length_z * 0.2], [s.Length / 2, s.Length_y / 2, s.Length_z * 0.2],
                      [3 * s.Length / 4, s.Length_y / 2, s.Length_z * 0.2]],
                     [[s.Length / 4, s.Length_y / 2, s.Length_z * 0.8], [s.Length / 2, s.Length_y / 2, s.Length_z * 0.8],
-                     [3 * s.Length / 4, s.Length_y / 2, s.Length_z * 0.8]])
-            if well_case in table and not (geo.dim == 2 and well_case == "default"):
+                     [3 * s.Length / 4, s.Length_y / 2, s.Length_z * 0.8]])}
+            if well_case in table:
                 pp, ip = table[well_case](self)
                 heater_points = pp + ip
         self.init_heaters(heater_points, "circle")

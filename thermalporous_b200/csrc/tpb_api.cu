@@ -326,6 +326,8 @@ int tpb_solver_defaults(int nphase, tpb_solver_opts* o) {
     o->mg_semi_theta = 0.5;
     o->mg_full_below = 0;
     o->mg_dd_stop = 0.1;
+    o->mg_coarse_scale = 0.5;
+    o->mg_smoother = TPB_MG_ZLINE;
     o->verbose = 0;
     return TPB_OK;
 }
@@ -333,7 +335,9 @@ int tpb_solver_defaults(int nphase, tpb_solver_opts* o) {
 int tpb_set_solver_opts(tpb_handle h, const tpb_solver_opts* o) {
     TPB_TRY(h)
     TPB_REQUIRE(h && o, TPB_ERR_ARG, "null argument");
-    TPB_REQUIRE(o->ksp_restart > 0 && o->ksp_max_it >= 0 && o->snes_max_it >= 0, TPB_ERR_ARG, "bad iteration limits");
+    TPB_REQUIRE(o->ksp_restart > 0 && o->ksp_restart <= 250 && o->ksp_max_it >= 0 && o->snes_max_it >= 0, TPB_ERR_ARG,
+                "bad iteration limits (ksp_restart must be in [1, 250])");
+    TPB_REQUIRE(o->ksp_type == TPB_KSP_GMRES || o->ksp_type == TPB_KSP_FGMRES, TPB_ERR_ARG, "ksp_type must be gmres (0) or fgmres (1)");
     TPB_REQUIRE(o->stage1 >= 0 && o->stage1 <= 3 && o->stage2 >= 0 && o->stage2 <= 2, TPB_ERR_ARG, "bad PC stage");
     TPB_REQUIRE(o->schur_pre >= 0 && o->schur_pre <= 3 && o->decoup >= 0 && o->decoup <= 4, TPB_ERR_ARG, "bad PC option");
     TPB_REQUIRE(!(o->stage1 == TPB_S1_CPTR && h->nphase == 1), TPB_ERR_UNSUPPORTED,

@@ -312,7 +312,11 @@ static void p2p_init(tpb_handle_s* h) {
     v.off_mg = off;
     off += 4 * v.mg_cap * 8;
     const size_t bytes = (size_t)off;
-    bool fine = cudaMalloc(&c->my_box, bytes) == cudaSuccess && cudaMemset(c->my_box, 0, bytes) == cudaSuccess;
+    // zeroed on the handle's stream (every consumer runs there; it is non-blocking, so the legacy default stream
+    // would not be ordered against it) and complete before any peer can learn the handle: the all-gather below
+    // synchronises the stream first
+    bool fine = cudaMalloc(&c->my_box, bytes) == cudaSuccess && cudaMemsetAsync(c->my_box, 0, bytes, h->stream) == cudaSuccess &&
+                cudaStreamSynchronize(h->stream) == cudaSuccess;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof(mine));
     fine = fine && cudaIpcGetMemHandle(&mine, c->my_box) == cudaSuccess;
@@ -323,7 +327,11 @@ static void p2p_init(tpb_handle_s* h) {
     std::vector<double> all((size_t)W * c->nranks, 0.0), me(W, 0.0);
     me[0] = fine ? 1.0 : 0.0;
     memcpy(&me[1], &mine, 64);
-    double* dev = tpb_dalloc<double>((size_t)W * c->nranks);
+    struct DevBuf {   // freed on every way out, including a throwing TPB_CUDA / TPB_NCCL
+        double* p;
+        ~DevBuf() { tpb_dfree(p); }
+    } devbuf{tpb_dalloc<double>((size_t)W * c->nranks)};
+    double* dev = devbuf.p;
     TPB_CUDA(cudaMemcpyAsync(dev + (size_t)W * c->rank, me.data(), W * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     TPB_NCCL(a.AllGather(dev + (size_t)W * c->rank, dev, (size_t)W, ncclFloat64, c->comm, h->stream));
     TPB_CUDA(cudaMemcpyAsync(all.data(), dev, all.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -352,14 +360,25 @@ static void p2p_init(tpb_handle_s* h) {
     TPB_NCCL(a.AllReduce(dev, dev, 1, ncclFloat64, ncclSum, c->comm, h->stream));
     TPB_CUDA(cudaMemcpyAsync(me.data(), dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     TPB_CUDA(cudaStreamSynchronize(h->stream));
-    tpb_dfree(dev);
-    if (me[0] != 0.0) return;   // some rank could not map a peer: NCCL paths stay in charge
+    if (me[0] != 0.0) {
+        // some rank could not map a peer: NCCL paths stay in charge; give the mailbox and the mappings back
+        for (int r = 0; r < c->nranks; r++)
+            if (c->peer_box[r]) {
+                cudaIpcCloseMemHandle(c->peer_box[r]);
+                c->peer_box[r] = nullptr;
+            }
+        tpb_dfree(c->my_box);
+        c->my_box = nullptr;
+        cudaGetLastError();
+        return;
+    }
     c->epoch = tpb_dalloc<unsigned long long>(P2P_NSLOT);
     c->err = tpb_dalloc<int>(1);
     c->ticket = tpb_dalloc<unsigned int>(4);   // [0] push/pull kernels, [1..3] fused halo kernels
-    TPB_CUDA(cudaMemset(c->epoch, 0, P2P_NSLOT * sizeof(unsigned long long)));
-    TPB_CUDA(cudaMemset(c->err, 0, sizeof(int)));
-    TPB_CUDA(cudaMemset(c->ticket, 0, 4 * sizeof(unsigned int)));
+    TPB_CUDA(cudaMemsetAsync(c->epoch, 0, P2P_NSLOT * sizeof(unsigned long long), h->stream));
+    TPB_CUDA(cudaMemsetAsync(c->err, 0, sizeof(int), h->stream));
+    TPB_CUDA(cudaMemsetAsync(c->ticket, 0, 4 * sizeof(unsigned int), h->stream));
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
     v.epoch = c->epoch;
     v.err = c->err;
     c->p2p_mask = mask;

@@ -177,7 +177,7 @@ class ThermalModel:
     nphase = 1
 
     def __init__(self, end=1.0, maxdt=0.005, save=False, n_save=2, small_dt_start=True, checkpointing=None,
-                 filename="results/results.txt", dt_init_fact=2 ** (-10), verbosity=True, device=0):
+                 filename="results/results.txt", dt_init_fact=2 ** (-10), verbosity=True, device=None):
         from .engine import Engine
         from . import _lib as L
         # thermalmodel.py:113-133,304-320: every n_save-th step the fields go to results/<field>.pvd; here a .pvd
@@ -202,6 +202,20 @@ class ThermalModel:
                 self.rank, self.world = dist.get_rank(), dist.get_world_size()
         except ImportError:
             pass
+        # The reference constructors have no device argument: under torchrun every rank must still end up on its own
+        # GPU.  device=None resolves to LOCAL_RANK (torchrun) when there are several ranks, else to torch's current
+        # device; ranks of one node sharing a device are refused before ncclCommInitRank would hang on them.
+        if device is None:
+            import torch
+            device = int(os.environ["LOCAL_RANK"]) if (self.world > 1 and "LOCAL_RANK" in os.environ) else torch.cuda.current_device()
+        if self.world > 1:
+            import socket
+            import torch.distributed as dist
+            mine = (socket.gethostname(), int(device))
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine)
+            if len(set(everyone)) != len(everyone):
+                raise RuntimeError("ranks share a GPU: %r - pass device=LOCAL_RANK (INTEGRATION.md)" % (everyone,))
         self.slab = slab = Slab(geo, self.world, self.rank)
         nxl, nyl, nzl = slab.local_dims()
         self.engine = Engine(geo.dim, nxl, nyl, nzl, geo.Dx, geo.Dy, getattr(geo, "Dz", 1.0), self.nphase, prm,

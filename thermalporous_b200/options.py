@@ -44,8 +44,6 @@ SINGLE_PHASE_SETS = {
     "pc_cpr_QI": ("singlephase.py:353", _two_stage(S1_CPR, "QI")),
     "pc_cpr_TI": ("singlephase.py:354", _two_stage(S1_CPR, "TI")),
     "pc_cpr_gmres": ("singlephase.py:356-369", _two_stage(S1_CPR)),
-    "pc_ilu": ("singlephase.py:388-391", _two_stage(S1_NONE)),
-    "pc_bilu": ("singlephase.py:402-406", _two_stage(S1_NONE)),
     # solver_parameters=None resolves to the unmatched name "pc_fieldsplit" => bare GMRES with PETSc's
     # default PC, which is (block-Jacobi) ILU(0)  (singlephase.py:410-413)
     "pc_fieldsplit": ("singlephase.py:412-413", _two_stage(S1_NONE)),
@@ -61,9 +59,7 @@ TWO_PHASE_SETS = {
     "pc_cpr_QI_temp": ("twophase.py:596", _two_stage(S1_CPR, "QI_temp")),
     "pc_cpr_TI_temp": ("twophase.py:597", _two_stage(S1_CPR, "TI_temp")),
     "pc_cpr_gmres": ("twophase.py:619-634", _two_stage(S1_CPR)),
-    "pc_cprilu1_gmres": ("twophase.py:653-668", _two_stage(S1_CPR)),   # ILU(1) realised as ILU(0)
     "pc_ilu": ("twophase.py:734-737", _two_stage(S1_NONE)),
-    "pc_bilu": ("twophase.py:757-762", _two_stage(S1_NONE)),
 }
 
 _UNSUPPORTED = {
@@ -73,18 +69,35 @@ _UNSUPPORTED = {
     "pc_cptramg_TI": "system AMG on (p,T)", "pc_cptramg_gmres": "system AMG on (p,T)",
     "pc_cptrlu": "direct solve of the (p,T) block", "pc_cptrlu_QI": "direct solve", "pc_cptrlu_TI": "direct solve",
     "pc_cptrlu_gmres": "direct solve", "pc_cprmg_gmres": "PCMG over a mesh hierarchy",
+    "pc_ilu": "ILU(1) in the single-phase model (pc_factor_levels 1, singlephase.py:388-391; ILU here is ILU(0))",
+    "pc_bilu": "ILU(1) (sub_pc_factor_levels 1, singlephase.py:402-406, twophase.py:757-762; ILU here is ILU(0))",
+    "pc_cprilu1_gmres": "ILU(1) second stage (twophase.py:653-668; the second stage here is ILU(0))",
     "faspardecomp": "FAS/PatchPC", "ngmresfaspardecomp": "FAS/PatchPC", "newtonaijfaspardecomp": "FAS/PatchPC",
     "newtonmgpardecomp": "FAS/PatchPC",
 }
 
 # keys of a raw PETSc dict that only switch monitoring / are implied
 _IGNORED_KEYS = {"snes_monitor", "snes_converged_reason", "ksp_converged_reason", "ksp_view", "snes_view",
-                 "ksp_monitor", "ksp_monitor_residuals", "ksp_monitor_true_residual", "mat_type", "snes_type",
-                 "ksp_pc_side", "pc_composite_type", "pc_composite_pcs", "sub_1_sub_pc_type",
-                 "sub_1_sub_pc_factor_levels", "sub_1_pc_bjacobi_blocks", "pc_factor_levels", "sub_pc_type",
-                 "sub_pc_factor_levels", "pc_fieldsplit_schur_fact_type"}
+                 "ksp_monitor", "ksp_monitor_true_residual", "mat_type", "snes_type",
+                 "ksp_pc_side", "pc_composite_type", "pc_composite_pcs", "sub_1_sub_pc_type", "sub_1_pc_type",
+                 "sub_1_pc_bjacobi_blocks", "sub_pc_type", "pc_type", "sub_0_pc_type", "sub_0_pc_python_type",
+                 "sub_0_cpr_decoup", "pc_fieldsplit_type", "pc_fieldsplit_schur_precondition",
+                 "pc_fieldsplit_0_fields", "pc_fieldsplit_1_fields", "sub_0_pc_fieldsplit_0_fields",
+                 "sub_0_pc_fieldsplit_1_fields", "sub_0_pc_fieldsplit_type"}
+# keys handled explicitly below
+_HANDLED_KEYS = {"ksp_type", "ksp_max_it", "ksp_gmres_restart", "ksp_rtol", "ksp_atol", "snes_max_it", "snes_rtol",
+                 "snes_atol", "snes_stol", "snes_linesearch_type", "sub_1_sub_pc_factor_levels", "pc_factor_levels",
+                 "sub_pc_factor_levels", "pc_fieldsplit_schur_fact_type", "sub_0_cpr_stage1_pc_fieldsplit_schur_fact_type",
+                 "ksp_monitor_residuals"}
+# The inner solvers of the first stage are libtpb200's own (one multigrid V-cycle per scalar block in the role of
+# hypre, tpb_* knobs): their PETSc/hypre tuning keys describe solvers that do not exist here and are accepted.
+_INNER_PREFIXES = ("sub_0_cpr_stage1_", "sub_0_fieldsplit_", "fieldsplit_", "pc_hypre_", "sub_0_pc_hypre_", "tpb_",
+                   "sub_0_ksp_", "sub_1_ksp_", "sub_0_sub_", "sub_1_sub_ksp_", "snes_npc_", "npc_", "snes_linesearch_max",
+                   "snes_linesearch_monitor", "pc_mg_", "mg_", "pc_ml_", "pc_gamg_")
 
-_LS = {"basic": 0, "bt": 1, "l2": 1, "cp": 1}
+# line searches: `basic` takes the full step; `bt` is the cubic back-tracking default of PETSc, realised as step halving
+# on the same sufficient-decrease test.  l2 / cp are secant searches on a different merit function: not realised.
+_LS = {"basic": 0, "bt": 1}
 
 
 def _flatten(d, prefix=""):
@@ -125,8 +138,6 @@ def _from_dict(d, nphase):
                 o.update(_two_stage(S1_CPR))
         else:
             raise UnsupportedOption("composite PC without a CPR/CPTR first stage")
-        if int(d.get("sub_1_sub_pc_factor_levels", 0)) not in (0, 1):
-            raise UnsupportedOption("ILU fill level > 1")
     elif pc_type == "fieldsplit":
         if nphase != 1:
             raise UnsupportedOption("top-level field-split option sets exist for the single-phase model only")
@@ -158,12 +169,27 @@ def _from_dict(d, nphase):
             o[name] = cast(d[key])
     if "snes_linesearch_type" in d:
         if d["snes_linesearch_type"] not in _LS:
-            raise UnsupportedOption("snes_linesearch_type %r" % d["snes_linesearch_type"])
+            raise UnsupportedOption("snes_linesearch_type %r (basic and bt are realised)" % d["snes_linesearch_type"])
         o["linesearch"] = _LS[d["snes_linesearch_type"]]
+    for key in ("sub_1_sub_pc_factor_levels", "pc_factor_levels", "sub_pc_factor_levels"):
+        if int(d.get(key, 0)) != 0:
+            raise UnsupportedOption("%s=%s: the second stage is ILU(0); ILU with fill is not realised" % (key, d[key]))
+    for key in ("pc_fieldsplit_schur_fact_type", "sub_0_cpr_stage1_pc_fieldsplit_schur_fact_type"):
+        if str(d.get(key, "FULL")).upper() != "FULL":
+            raise UnsupportedOption("%s=%s: only the FULL Schur factorisation is realised (twophase.py:539)" % (key, d[key]))
+    if d.get("ksp_monitor_residuals") not in (None, False):
+        raise UnsupportedOption("ksp_monitor_residuals: the per-field residual monitor (thermalmodel.py:44-74) is not realised; "
+                                "use tpb_verbose=2 for the Krylov residual history")
     # our own multigrid / smoother knobs may be passed with a tpb_ prefix
     for k, v in d.items():
         if k.startswith("tpb_"):
             o[k[4:]] = v
+    # no silent fall-back: a key that is neither handled, nor known to be implied, nor tuning of an inner solver that
+    # libtpb200 replaces is an error (typos such as 'ksp_rtoll' used to be dropped)
+    for k in d:
+        if k in _HANDLED_KEYS or k in _IGNORED_KEYS or k.startswith(_INNER_PREFIXES):
+            continue
+        raise UnsupportedOption("unrecognised solver option %r" % k)
     return o
 
 
