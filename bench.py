@@ -362,8 +362,8 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)     # the driver's own run: 20 steps after 5 warm-up, which takes
+    ap.add_argument("--warmup", type=int, default=5)     # dt from the small_dt_start phase up to ~0.1 day
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scale", default="stack", choices=["stack", "refine"], help="how the grid grows with --gpus (weak scaling)")

@@ -840,13 +840,14 @@ static void mg_vcycle_level(const tpc_handle_s* h, mghier* m, int l) {
         return;
     }
     int pre = o->mg_pre > 0 ? o->mg_pre : 1;
+    const int post = o->mg_post;
     for (int s = 0; s < pre; s++) mg_smooth(L, ns, L->b, L->x, s == 0);
     mg_residual(L, ns, L->b, L->x, L->r);
     mglevel* Cc = &m->lev[l + 1];
     mg_restrict(L, Cc, L->r, Cc->b);
     mg_vcycle_level(h, m, l + 1);
     mg_prolong_add(L, Cc, Cc->x, L->x, o->mg_overcorrection);
-    for (int s = 0; s < o->mg_post; s++) mg_smooth(L, ns, L->b, L->x, 0);
+    for (int s = 0; s < post; s++) mg_smooth(L, ns, L->b, L->x, 0);
 }
 
 /* y = V(b): mg_cycles V-cycles from a zero initial guess */

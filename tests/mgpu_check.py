@@ -47,8 +47,8 @@ eJ = rel(J.cpu().numpy(), Jc[..., slab.c0:slab.c1])
 ey = max(rel(y.cpu().numpy()[f], slab.take(yc)[f]) for f in range(3))
 # Newton from the uniform state, one small step
 opts, _, _ = O.resolve("pc_cptr", 2)
-# mg_dd_stop acts on single-rank handles only unless TPB_MG_DD_DIST=1: the single-domain CPU run follows the slabs
-DD = {} if os.environ.get("TPB_MG_DD_DIST", "0") != "0" else {"mg_dd_stop": 0.0}
+# mg_dd_stop acts on slabs as on a single domain unless TPB_MG_DD_DIST=0: the single-domain CPU run follows the slabs
+DD = {} if os.environ.get("TPB_MG_DD_DIST", "1") != "0" else {"mg_dd_stop": 0.0}
 opts.update(snes_rtol=1e-11, snes_stol=1e-13, ksp_rtol=1e-6, snes_max_it=40, **DD)
 eng.set_solver_opts(**opts); cpu.set_solver_opts(**opts)
 u0 = np.stack([np.full(n, prm.p_ref), np.full(n, prm.T_prod), np.full(n, 0.9)])

@@ -46,6 +46,17 @@ COMBOS = [
     (2, 3, (9, 11, 14), dict(stage1=cport.S1_CPTR, decoup=0, mg_dd_stop=0.0)),
     (2, 3, (9, 11, 14), dict(stage1=cport.S1_CPTR, decoup=1, mg_dd_stop=0.5)),
     (2, 3, (6, 13, 10), dict(stage1=cport.S1_CPTR, decoup=1, mg_dd_stop=1e9)),
+    # 3-D combos above run the default smoother (zebra z-line, z never coarsened, coarse couplings scaled by 0.5);
+    # the point smoother / plain Galerkin paths: red-black Gauss-Seidel with z coarsened like any other axis
+    (2, 3, (9, 11, 14), dict(stage1=cport.S1_CPTR, decoup=0, mg_smoother=0)),
+    (2, 3, (9, 11, 14), dict(stage1=cport.S1_CPTR, decoup=1, mg_smoother=0, mg_coarse_scale=1.0)),
+    (1, 3, (6, 10, 12), dict(stage1=cport.S1_CPR, decoup=1, mg_smoother=0, mg_coarse_scale=1.0)),
+    (2, 3, (20, 24, 40), dict(stage1=cport.S1_CPTR, decoup=1, mg_smoother=0, mg_cycles=2)),
+    (2, 2, (1, 24, 17), dict(stage1=cport.S1_CPTR, decoup=1, mg_coarse_scale=1.0)),
+    # z-line tiles: more columns per colour than one 32-column tile, tall columns, odd sizes
+    (2, 3, (85, 70, 33), dict(stage1=cport.S1_CPTR, decoup=0)),
+    (2, 3, (130, 9, 7), dict(stage1=cport.S1_CPR, decoup=1, mg_pre=1, mg_post=1)),
+    (1, 3, (300, 3, 2), dict(stage1=cport.S1_CPR, decoup=0)),
 ]
 TOL = 1e-10
 

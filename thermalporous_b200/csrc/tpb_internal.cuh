@@ -88,11 +88,20 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // launch with programmatic stream serialisation; TPB_PDL=0 launches normally
 bool tpb_pdl_enabled();
 template <typename... KArgs, typename... Args>
+inline void launch_pdl_smem(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                            Args... args);
+template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    launch_pdl_smem(kernel, grid, block, 0, st, args...);
+}
+// the same with dynamic shared memory (kernels that need more than 48 KB opt in once with cudaFuncSetAttribute)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl_smem(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                            Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(block, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -8,8 +8,12 @@
 //   K4  ConvDiff temperature operator with coefficients frozen at the Newton state
 //   K7  scalar-stencil multigrid V-cycle in the role of hypre BoomerAMG (one V-cycle per apply):
 //       piecewise-constant aggregation with per-level semi-coarsening (an axis is coarsened only
-//       where its mean coupling is strong), Galerkin coarse operators (stay 5|7-point), red-black
-//       Gauss-Seidel smoothing; the coarsest levels (<= TAIL_CELLS cells) run inside one CTA.
+//       where its mean coupling is strong), Galerkin coarse operators (stay 5|7-point) with the
+//       couplings along coarsened axes scaled by mg_coarse_scale (cell-centred multigrid: the plain
+//       Galerkin operator of constant transfers is 2x too stiff per coarsened axis); smoothing by
+//       zebra z-line Gauss-Seidel in 3-D (every column solved exactly from factors computed at
+//       set-up, z never coarsened - thin layers, Dz << Dx) or red-black point Gauss-Seidel (2-D,
+//       mg_smoother 0); the coarsest levels (<= TAIL_CELLS cells) run inside one CTA.
 // Stage 2 (reference: PETSc bjacobi + ilu(0), singlephase.py:348-349, twophase.py:547-548):
 //   K8  block ILU(0) of the nf x nf block stencil in red-black ordering: for a 5|7-point stencil
 //       ILU(0) only modifies the diagonal blocks, D_b = A_bb - sum_r A_br A_rr^-1 A_rb, and both
@@ -37,6 +41,9 @@ struct MgLevel {
     double* b = nullptr;  // multi-rank hierarchy) this rank's section of the gathered level
     double* x_own = nullptr;
     double* b_own = nullptr;
+    bool line = false;    // smoothed by zebra z-line Gauss-Seidel
+    double* fac = nullptr;   // 3 * cap: Thomas factors of every column (1/pivot | lower/pivot | upper/pivot)
+    long long fac_cap = 0;
 };
 
 // Multi-rank slabs (K7 over NCCL): every rank coarsens its own slab with globally agreed coarsening factors
@@ -58,11 +65,11 @@ struct MgHier {
     bool skip_glob = false;        // multi-rank hierarchy that stopped on diagonal dominance: no gather level this set-up
 };
 
-// mg_dd_stop on multi-rank slabs (TPB_MG_DD_DIST=1; off until it has been run on more than one GPU): the row ratio is
-// max-reduced over the ranks, so all of them stop at the same level, and a hierarchy that stopped this way has no
-// gather level - its last level is smoothed slab by slab like the levels above it
+// mg_dd_stop on multi-rank slabs (TPB_MG_DD_DIST=0 switches it off): the row ratio is max-reduced over the ranks, so
+// all of them stop at the same level, and a hierarchy that stopped this way has no gather level - its last level is
+// smoothed slab by slab like the levels above it
 inline bool dd_on_slabs() {
-    static const bool v = getenv("TPB_MG_DD_DIST") && atoi(getenv("TPB_MG_DD_DIST")) != 0;
+    static const bool v = !(getenv("TPB_MG_DD_DIST") && atoi(getenv("TPB_MG_DD_DIST")) == 0);
     return v;
 }
 
@@ -411,6 +418,7 @@ __global__ void convdiff_sources_kernel(int ncells, const int64_t* __restrict__ 
 struct LevGeom {
     int nx, ny, nz, cx, cy, cz;   // cx,cy,cz in {1,2}: aggregate index = fine index >> (c - 1)
     long long n;
+    int line;                     // z-line smoothed level: colours are (i+j)&1 columns instead of (i+j+k)&1 cells
 };
 
 // clamped neighbour for branch-free stencil sweeps: index of the neighbour through slot s, or the cell itself
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(256) row_repair_kernel(double* __restrict__ a,
 // Galerkin coarse operator for piecewise-constant aggregates (stays a 5|7-point stencil)
 template <int NS>
 __global__ void __launch_bounds__(128) coarsen_op_kernel(const double* __restrict__ af, LevGeom f, LevGeom cg,
-                                                         double* __restrict__ ac) {
+                                                         double sc, double* __restrict__ ac) {
     long long C = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (C >= cg.n) return;
     int I, Jc, Kc;
@@ -518,8 +526,180 @@ __global__ void __launch_bounds__(128) coarsen_op_kernel(const double* __restric
                     if (same) acc[0] += v; else acc[s] += v;
                 }
             }
+    // tpb_solver_opts.mg_coarse_scale: couplings along a coarsened axis are scaled, the row sum is kept
+    if (sc != 1.0) {
+#pragma unroll
+        for (int s = 1; s < NS; s++) {
+            const int axis = (s - 1) >> 1;
+            const int cf = axis == 0 ? f.cx : (axis == 1 ? f.cy : f.cz);
+            if (cf == 2) {
+                const double nv = sc * acc[s];
+                acc[0] += acc[s] - nv;
+                acc[s] = nv;
+            }
+        }
+    }
 #pragma unroll
     for (int s = 0; s < NS; s++) ac[(long long)s * cg.n + C] = acc[s];
+}
+
+// ---- zebra z-line Gauss-Seidel (3-D levels) ------------------------------------------------------
+// LU factors of every column's tridiagonal (diag, z-, z+), one thread per column marching up: id = 1/pivot,
+// lf = lower * id, cp = upper * id.  The couplings through the bottom and the top of the box (slab faces on
+// multi-rank runs) are not part of the column.  Same arithmetic as oracle/cport mg_line_factors.
+__global__ void __launch_bounds__(128) line_factor_kernel(const double* __restrict__ a, LevGeom g, double* __restrict__ fac) {
+    const long long np = (long long)g.nx * g.ny, n = g.n;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= np) return;
+    double cprev = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < g.nz; k++) {
+        const long long c = q + np * k;
+        const double lo = k > 0 ? a[5 * n + c] : 0.0, up = k < g.nz - 1 ? a[6 * n + c] : 0.0;
+        const double den = a[c] - lo * cprev;
+        const double id = den != 0.0 ? 1.0 / den : 0.0;
+        fac[c] = id;
+        fac[n + c] = lo * id;
+        cprev = up * id;
+        fac[2 * n + c] = cprev;
+    }
+}
+
+// One colour of a zebra sweep for a tile of `cpc` (<= 32) columns held in shared memory:
+//   phase A (all threads, one cell per trip): e = (b - sum over the four lateral neighbours) * id -> smem, and the
+//            factors lf, cp -> smem.  Every load is independent of the recurrences, blocks are large (up to 1024
+//            threads) so that a tile is one or two trips: the memory round trips of a pass overlap instead of queueing;
+//   phase B (one warp per column): both first-order recurrences d_k = e_k - lf_k d_{k-1} (up) and
+//            x_k = d_k - cp_k x_{k+1} (down) as warp scans over affine maps, 32 levels of the column per round with the
+//            carry broadcast from the last lane - 5 shuffle steps per round instead of a chain of nz dependent FMAs;
+//   phase C (all threads): x written back.
+// Shared layout: [column][k], column stride nzp = nz | 1 doubles (odd: phase A's column-fastest stores and phase B's
+// k-fastest loads are both free of bank conflicts).
+// Column slot t of the colour: j = t / nxh, i = 2 (t % nxh) + ((col + j) & 1), as the point smoother enumerates cells.
+// PROLONG / zero_guess as in rbgs_cell: a line update never reads its own column's old values, so the coarse
+// correction of the other colour's columns is formed on the fly.
+struct LineTile {
+    double *e, *lf, *cp;   // [cpc][nzp]
+    int nzp;
+};
+__host__ __device__ __forceinline__ int line_nzp(int nz) { return nz | 1; }
+__device__ __forceinline__ LineTile line_tile(double* sm, int nz, int cpc) {
+    const int nzp = line_nzp(nz);
+    return LineTile{sm, sm + (size_t)nzp * cpc, sm + 2 * (size_t)nzp * cpc, nzp};
+}
+
+// inclusive warp scan of the affine maps v -> M v + C (composition order: lower lanes first)
+__device__ __forceinline__ void affine_scan(double& M, double& C, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double Mp = __shfl_up_sync(0xffffffffu, M, off);
+        const double Cp = __shfl_up_sync(0xffffffffu, C, off);
+        if (lane >= off) {
+            C = fma(M, Cp, C);
+            M = M * Mp;
+        }
+    }
+}
+
+template <bool PROLONG>
+__device__ __forceinline__ void line_tile_pass(const double* __restrict__ a, const double* __restrict__ fac,
+                                               const double* b, double* x, const LevGeom& g, int col, bool zero_guess,
+                                               const double* xc, int cnx, int cny, double omega, int q0, int cpc,
+                                               int lg2, const LineTile& T, int tid, int nth, bool static_first) {
+    const int nz = g.nz, nxh = (g.nx + 1) >> 1, ncol = nxh * g.ny;
+    const long long n = g.n, np = (long long)g.nx * g.ny;
+    const int tile = nz * cpc;
+    if (static_first) pdl_wait();
+    for (int idx = tid; idx < tile; idx += nth) {
+        const int k = idx / cpc, qq = idx - k * cpc, t = q0 + qq;
+        bool act = t < ncol;
+        int i = 0, j = 0;
+        if (act) {
+            j = t / nxh;
+            i = 2 * (t - j * nxh) + ((col + j) & 1);
+            act = i < g.nx;
+        }
+        double e = 0.0, lf = 0.0, cp = 0.0;
+        if (act) {
+            const long long c = i + (long long)g.nx * j + np * k;
+            lf = fac[n + c];
+            cp = fac[2 * n + c];
+            const double id = fac[c];
+            double rhs = b[c];
+            if (!zero_guess) {
+                double tt[4];
+#pragma unroll
+                for (int s = 1; s < 5; s++) {
+                    bool ex;
+                    const long long nb = nbr_clamped(g.nx, g.ny, g.nz, i, j, k, c, s, ex);
+                    double xv = x[nb];
+                    if (PROLONG) {
+                        const int d = ((s - 1) & 1) ? 1 : -1;
+                        const int ii = (ex && s < 3) ? i + d : i, jj = (ex && s >= 3) ? j + d : j;
+                        xv += omega * xc[(ii >> (g.cx - 1)) + (long long)cnx * ((jj >> (g.cy - 1)) + (long long)cny * (k >> (g.cz - 1)))];
+                    }
+                    const double p = a[(long long)s * n + c] * xv;
+                    tt[s - 1] = ex ? p : 0.0;
+                }
+#pragma unroll
+                for (int s = 0; s < 4; s++) rhs -= tt[s];
+            }
+            e = rhs * id;
+        }
+        const int o = qq * T.nzp + k;
+        T.e[o] = e;
+        T.lf[o] = lf;
+        T.cp[o] = cp;
+    }
+    __syncthreads();
+    {
+        const int lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
+        for (int qq = wid; qq < cpc; qq += nw) {
+            double* ev = T.e + qq * T.nzp;
+            const double* lv = T.lf + qq * T.nzp;
+            const double* cv = T.cp + qq * T.nzp;
+            double carry = 0.0;
+            for (int k0 = 0; k0 < nz; k0 += 32) {          // up: d_k = e_k - lf_k d_{k-1}
+                const int k = k0 + lane;
+                double M = k < nz ? -lv[k] : 1.0, C = k < nz ? ev[k] : 0.0;
+                affine_scan(M, C, lane);
+                const double d = fma(M, carry, C);
+                if (k < nz) ev[k] = d;
+                carry = __shfl_sync(0xffffffffu, d, 31);
+            }
+            __syncwarp();
+            carry = 0.0;
+            for (int r0 = 0; r0 < nz; r0 += 32) {          // down: x_k = d_k - cp_k x_{k+1}, walked as r = nz-1-k
+                const int k = nz - 1 - (r0 + lane);
+                double M = k >= 0 ? -cv[k] : 1.0, C = k >= 0 ? ev[k] : 0.0;
+                affine_scan(M, C, lane);
+                const double xk = fma(M, carry, C);
+                if (k >= 0) ev[k] = xk;
+                carry = __shfl_sync(0xffffffffu, xk, 31);
+            }
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < tile; idx += nth) {
+        const int k = idx / cpc, qq = idx - k * cpc, t = q0 + qq;
+        if (t < ncol) {
+            const int j = t / nxh, i = 2 * (t - j * nxh) + ((col + j) & 1);
+            if (i < g.nx) x[i + (long long)g.nx * j + np * k] = T.e[qq * T.nzp + k];
+        }
+    }
+}
+
+constexpr int ZL_THREADS = 1024;
+template <bool PROLONG>
+__global__ void __launch_bounds__(ZL_THREADS) zline_kernel(const double* __restrict__ a, const double* __restrict__ fac,
+                                                           const double* b, double* x, LevGeom g, int col, int zero_guess,
+                                                           const double* xc, int cnx, int cny, double omega, int cpc,
+                                                           int lg2) {
+    extern __shared__ double zl_sm[];
+    pdl_launch_dependents();
+    const LineTile T = line_tile(zl_sm, g.nz, cpc);
+    line_tile_pass<PROLONG>(a, fac, b, x, g, col, zero_guess != 0, xc, cnx, cny, omega, (int)blockIdx.x * cpc, cpc, lg2, T,
+                            (int)threadIdx.x, (int)blockDim.x, true);
 }
 
 // one colour of a red-black Gauss-Seidel sweep: colour = (i+j+k)&1.  Threads walk the cells of the
@@ -612,7 +792,8 @@ __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a,
 // fully unrolled 2x2x2 box; the summation order (k, j, i; within a cell diag, x-, x+, ...) is the one the CPU
 // restatement uses.
 // Only the cells of colour 0 contribute: the restriction always follows a pre-smoothing sweep whose last pass
-// updated colour 1, and a Gauss-Seidel update leaves a zero residual in the row it solved - half of the loads.
+// updated colour 1 (cells with (i+j+k)&1, or whole columns with (i+j)&1 on a line-smoothed level), and a
+// Gauss-Seidel update leaves a zero residual in the rows it solved - half of the loads.
 template <int NS>
 __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, const double* b, const double* x,
                                                 const LevGeom& f, int I, int Jc, int Kc) {
@@ -621,7 +802,8 @@ __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, co
     for (int q = 0; q < 8; q++) {
         const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
         const int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
-        const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + k) & 1) == 0;
+        const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz &&
+                        ((i + j + (f.line ? 0 : k)) & 1) == 0;
         r[q] = 0.0;
         if (ok) {
             long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
@@ -659,7 +841,7 @@ __global__ void __launch_bounds__(256) restrict_kernel(const double* __restrict_
         tpb_ijk(C, cg.nx, cg.ny, I, Jc, Kc);
         const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
         i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
-        ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + k) & 1) == 0;
+        ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + (f.line ? 0 : k)) & 1) == 0;
     }
     pdl_launch_dependents();
     const long long c = ok ? i + (long long)f.nx * (j + (long long)f.ny * k) : 0;
@@ -716,12 +898,14 @@ __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict_
 
 // ---- the coarse tail: every level from `l0` down runs inside ONE CTA (levels of <= TAIL_CELLS cells) ---
 constexpr int TAIL_CELLS = 4096;
-constexpr int TAIL_THREADS = 512;
+constexpr int TAIL_THREADS = 1024;
 struct TailLevel {
     LevGeom g;
     const double* a;
     double* x;
     double* b;
+    const double* fac;   // line-smoothed levels: Thomas factors
+    int cpc, lg2;        // columns per shared-memory tile (power of two) and its log2
 };
 struct TailArgs {
     int nlev;
@@ -740,11 +924,30 @@ struct BlockBarrier {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
+extern __shared__ double tail_sm[];
+
 template <int NS, bool PROLONG, class Barrier>
 __device__ __forceinline__ void cyc_sweep(const TailLevel& L, bool zero_guess, const double* xc, int cnx, int cny,
                                           double omega, long long tid, long long nth, Barrier& bar) {
     const LevGeom& g = L.g;
     const int nxh = (g.nx + 1) >> 1;
+    if (NS == 7 && g.line) {
+        // zebra z-line sweep: the colour's columns in tiles of L.cpc through the block's shared memory
+        const int ncol = nxh * g.ny;
+        const LineTile T = line_tile(tail_sm, g.nz, L.cpc);
+        for (int col = 0; col < 2; col++) {
+            for (int q0 = 0; q0 < ncol; q0 += L.cpc) {
+                if (PROLONG && col == 0)
+                    line_tile_pass<true>(L.a, L.fac, L.b, L.x, g, col, false, xc, cnx, cny, omega, q0, L.cpc, L.lg2, T, (int)tid,
+                                         (int)nth, false);
+                else
+                    line_tile_pass<false>(L.a, L.fac, L.b, L.x, g, col, zero_guess && col == 0, nullptr, 0, 0, 0.0, q0, L.cpc,
+                                          L.lg2, T, (int)tid, (int)nth, false);
+                bar();
+            }
+        }
+        return;
+    }
     const long long total = (long long)g.ny * g.nz * nxh;
     for (int col = 0; col < 2; col++) {
         for (long long t = tid; t < total; t += nth) {
@@ -1091,13 +1294,14 @@ __global__ void __launch_bounds__(256) bjacobi_kernel(const double* __restrict__
 // =================================================================================================
 inline unsigned nblk(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
-inline LevGeom lg(const MgLevel& L) { return LevGeom{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.n}; }
+inline LevGeom lg(const MgLevel& L) { return LevGeom{L.nx, L.ny, L.nz, L.cx, L.cy, L.cz, L.n, L.line ? 1 : 0}; }
 
 void mg_free_levels(MgHier& m) {
     for (int l = 0; l < m.nlev; l++) {
         if (m.lev[l].own_a) tpb_dfree(m.lev[l].a);
         tpb_dfree(m.lev[l].x_own);
         tpb_dfree(m.lev[l].b_own);
+        tpb_dfree(m.lev[l].fac);
         m.lev[l] = MgLevel();
     }
     m.nlev = 0;
@@ -1126,10 +1330,36 @@ long long gather_cells() {
 // slab; coarsening factors are agreed between the ranks (all-reduced coupling sums, the largest slab decides
 // whether the slab axis can still be halved) and coarsening stops at the gather level.  planes: owned planes of
 // every rank along the slab axis, updated to the last level built.
+// Columns per zebra-line tile: as many as give one cell per thread of a ZL_THREADS block (nz = 85: 12 columns,
+// 1020 cells), at most 32 (one warp per column in the solve phase), within the shared-memory budget of 3 arrays
+// [cpc][nz | 1]; 0 when not even one column fits.
+constexpr size_t LINE_SMEM_BUDGET = 200 * 1024;
+inline int line_cpc(int nz, long long cols_per_colour, long long /*min_ctas*/) {
+    int cpc = std::max(1, std::min(32, ZL_THREADS / std::max(nz, 1)));
+    if (cols_per_colour > 0 && cpc > cols_per_colour) cpc = (int)cols_per_colour;
+    while (cpc > 1 && (size_t)3 * line_nzp(nz) * cpc * sizeof(double) > LINE_SMEM_BUDGET) cpc--;
+    if ((size_t)3 * line_nzp(nz) * cpc * sizeof(double) > LINE_SMEM_BUDGET) return 0;
+    return cpc;
+}
+inline int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
+}
+// threads of a zebra-line block: one per cell of the tile, whole warps, at most ZL_THREADS
+inline unsigned line_threads(int nz, int cpc) {
+    const long long t = ((long long)nz * cpc + 31) / 32 * 32;
+    return (unsigned)std::min<long long>(t, ZL_THREADS);
+}
+inline size_t line_smem(int nz, int cpc) { return (size_t)3 * line_nzp(nz) * cpc * sizeof(double); }
+
 template <int NS>
 void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int nz0, bool dist, std::vector<int>& planes) {
     PcState* pc = h->pc;
     const tpb_solver_opts& o = h->opts;
+    // zebra z-line smoothing on every level of a 3-D hierarchy (z is then never coarsened); falls back to the point
+    // smoother when a single column does not fit into shared memory
+    const bool line = NS == 7 && o.mg_smoother == TPB_MG_ZLINE && nz0 > 1 && line_cpc(nz0, 1, 0) > 0;
     // geometry of level 0 never changes between set-ups, and the coarsening schedule is recomputed from
     // the operator each time (as hypre's set-up is, preconditioners.py:878), so levels are re-allocated
     // only when their shape changes
@@ -1152,6 +1382,12 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
                 L.own_a = true;
             }
         }
+        L.line = line;
+        if (line && L.fac_cap < L.cap) {
+            tpb_dfree(L.fac);
+            L.fac = tpb_dalloc<double>((size_t)3 * L.cap);
+            L.fac_cap = L.cap;
+        }
         L.x = L.x_own;
         L.b = L.b_own;
         L.nx = nx;
@@ -1169,6 +1405,14 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
     for (;;) {
         MgLevel& L = nw.lev[l];
         L.cx = L.cy = L.cz = 1;
+        if (line) {
+            line_factor_kernel<<<nblk((long long)L.nx * L.ny, 128), 128, 0, h->stream>>>(L.a, lg(L), L.fac);
+            h->launches++;
+            if (L.nx == 1 && L.ny == 1) {   // a single column: the line solve is exact
+                nw.last_sweeps = 1;
+                break;
+            }
+        }
         int dims[3] = {L.nx, L.ny, L.nz};
         long long nglob = L.n;
         if (dist) {
@@ -1198,6 +1442,7 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
             nw.last_sweeps = dd_sweeps(m_ax[3], o.mg_coarse_sweeps);
             break;
         }
+        if (line) dims[2] = 1;   // z-line smoothing: z is never coarsened
         double mmax = 0.0;
         for (int ax = 0; ax < 3; ax++)
             if (dims[ax] > 1 && m_ax[ax] > mmax) mmax = m_ax[ax];
@@ -1222,7 +1467,8 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
         if (dist)
             for (int& p : planes) p = (p + cf[sax] - 1) / cf[sax];
         MgLevel& Cc = nw.lev[l + 1];
-        coarsen_op_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, lg(L), lg(Cc), Cc.a);
+        coarsen_op_kernel<NS><<<nblk(Cc.n, 128), 128, 0, h->stream>>>(L.a, lg(L), lg(Cc),
+                                                                     o.mg_coarse_scale > 0.0 ? o.mg_coarse_scale : 1.0, Cc.a);
         h->launches++;
         l++;
     }
@@ -1287,9 +1533,41 @@ void mg_setup(tpb_handle_s* h, MgHier& m, double* a0) {
         mg_setup_t<5>(h, m, a0);
 }
 
+// kernels with more than 48 KB of dynamic shared memory opt in once per process
+template <typename K>
+void want_smem(K kernel, size_t bytes) {
+    static std::vector<std::pair<const void*, size_t>> done;
+    for (auto& d : done)
+        if (d.first == (const void*)kernel && d.second >= bytes) return;
+    TPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bytes, 48 * 1024)));
+    done.push_back({(const void*)kernel, bytes});
+}
+
+// one smoothing sweep = two colour passes: zebra z-line on line-smoothed levels, red-black points otherwise
 template <int NS>
 void mg_rbgs(tpb_handle_s* h, const MgLevel& L, bool zero_guess, const MgLevel* coarse = nullptr, double omega = 0.0) {
     LevGeom g = lg(L);
+    if (L.line) {
+        const long long ncol = (long long)L.ny * ((L.nx + 1) >> 1);
+        const int cpc = line_cpc(L.nz, ncol, 2 * 148);
+        const int l2 = ilog2(cpc);
+        const size_t smem = line_smem(L.nz, cpc);
+        const unsigned grid = nblk(ncol, cpc);
+        const unsigned zt = line_threads(L.nz, cpc);
+        for (int col = 0; col < 2; col++) {
+            if (coarse && col == 0) {
+                want_smem(zline_kernel<true>, smem);
+                launch_pdl_smem(zline_kernel<true>, grid, zt, smem, h->stream, L.a, L.fac, L.b, L.x, g, col, 0, coarse->x,
+                                coarse->nx, coarse->ny, omega, cpc, l2);
+            } else {
+                want_smem(zline_kernel<false>, smem);
+                launch_pdl_smem(zline_kernel<false>, grid, zt, smem, h->stream, L.a, L.fac, L.b, L.x, g, col,
+                                (zero_guess && col == 0) ? 1 : 0, nullptr, 0, 0, 0.0, cpc, l2);
+            }
+            h->launches++;
+        }
+        return;
+    }
     long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
     for (int col = 0; col < 2; col++) {
         if (coarse && col == 0)
@@ -1314,6 +1592,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     int ltail = m.nlev;
     while (ltail > 0 && m.lev[ltail - 1].n <= TAIL_CELLS) ltail--;
     const int lcoop = std::min(ltail, dist ? last : m.nlev);
+    size_t tail_smem = 0;   // dynamic shared memory the single-CTA kernels of this cycle need (line tiles)
     auto tail_args_of = [&](MgHier& mm, int l0) {
         TailArgs A;
         A.nlev = mm.nlev - l0;
@@ -1322,6 +1601,15 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
             A.lev[l - l0].a = mm.lev[l].a;
             A.lev[l - l0].x = mm.lev[l].x;
             A.lev[l - l0].b = mm.lev[l].b;
+            A.lev[l - l0].fac = mm.lev[l].fac;
+            A.lev[l - l0].cpc = 1;
+            A.lev[l - l0].lg2 = 0;
+            if (mm.lev[l].line) {
+                const int cpc = line_cpc(mm.lev[l].nz, (long long)mm.lev[l].ny * ((mm.lev[l].nx + 1) >> 1), 0);
+                A.lev[l - l0].cpc = cpc;
+                A.lev[l - l0].lg2 = ilog2(cpc);
+                tail_smem = std::max(tail_smem, line_smem(mm.lev[l].nz, cpc));
+            }
         }
         A.pre = pre;
         A.post = o.mg_post;
@@ -1343,20 +1631,25 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     }
     if (!dist) {
         if (ltail < m.nlev) {
-            launch_pdl(tail_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));
+            const TailArgs A = tail_args(ltail);
+            want_smem(tail_kernel<NS>, tail_smem);
+            launch_pdl_smem(tail_kernel<NS>, 1, TAIL_THREADS, tail_smem, h->stream, A);
             h->launches++;
         }
     } else if (P2PView pv; m.glob->lev[0].n <= TAIL_CELLS && tpb_p2p_view(h, 4, &pv) &&
                            m.goff.back() + m.gcnt.back() <= pv.mg_cap) {
         // slab tail + gather + gathered hierarchy + way back up in one single-CTA kernel (tail_dist_kernel)
         const int rank = tpb_comm_rank(h);
-        launch_pdl(tail_dist_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(std::min(ltail, last)),
-                   tail_args_of(*m.glob, 0), pv, &m == &h->pc->mg_T ? 1 : 0, m.glob->lev[0].b, m.goff[rank], m.gcnt[rank],
-                   m.goff.back() + m.gcnt.back());
+        const TailArgs A = tail_args(std::min(ltail, last)), G = tail_args_of(*m.glob, 0);
+        want_smem(tail_dist_kernel<NS>, tail_smem);
+        launch_pdl_smem(tail_dist_kernel<NS>, 1, TAIL_THREADS, tail_smem, h->stream, A, G, pv, &m == &h->pc->mg_T ? 1 : 0,
+                        m.glob->lev[0].b, m.goff[rank], m.gcnt[rank], m.goff.back() + m.gcnt.back());
         h->launches++;
     } else {
         if (ltail < last) {
-            launch_pdl(tail_down_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));
+            const TailArgs A = tail_args(ltail);
+            want_smem(tail_down_kernel<NS>, tail_smem);
+            launch_pdl_smem(tail_down_kernel<NS>, 1, TAIL_THREADS, tail_smem, h->stream, A);
             h->launches++;
         }
         MgHier* mp = &m;
@@ -1369,7 +1662,9 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
             });
         mg_vcycle_t<NS>(h, *m.glob);
         if (ltail < last) {
-            launch_pdl(tail_up_kernel<NS>, 1, TAIL_THREADS, h->stream, tail_args(ltail));
+            const TailArgs A = tail_args(ltail);
+            want_smem(tail_up_kernel<NS>, tail_smem);
+            launch_pdl_smem(tail_up_kernel<NS>, 1, TAIL_THREADS, tail_smem, h->stream, A);
             h->launches++;
         }
     }
@@ -1793,11 +2088,24 @@ void tpb_pc_stage2_apply_impl(tpb_handle_s* h, const double* r, double* z) {
 }
 const double* tpb_pc_weights_impl(tpb_handle_s* h, int f) { return h->pc ? h->pc->w[f] : nullptr; }
 
-// one colour pass of the fine-level pressure smoother on its own (bench.py roofline of the dominant kernel)
+// one colour pass of the fine-level pressure smoother on its own (bench.py roofline of the dominant kernel);
+// returns the number of cells the pass updates
 long long tpb_pc_rbgs_pass_impl(tpb_handle_s* h, int col) {
     TPB_REQUIRE(h->pc && h->pc->ready && h->pc->mg_p.nlev > 0, TPB_ERR_STATE, "pressure multigrid not set up");
     const MgLevel& L = h->pc->mg_p.lev[0];
     LevGeom g = lg(L);
+    if (L.line) {
+        const long long ncol = (long long)L.ny * ((L.nx + 1) >> 1);
+        const int cpc = line_cpc(L.nz, ncol, 2 * 148);
+        const size_t smem = line_smem(L.nz, cpc);
+        want_smem(zline_kernel<false>, smem);
+        launch_pdl_smem(zline_kernel<false>, nblk(ncol, cpc), line_threads(L.nz, cpc), smem, h->stream, L.a, L.fac, L.b, L.x, g, col, 0,
+                        nullptr, 0, 0, 0.0, cpc, ilog2(cpc));
+        h->launches++;
+        long long cols = 0;   // columns of this colour
+        for (int j = 0; j < L.ny; j++) cols += (L.nx + 1 - ((col + j) & 1)) / 2;
+        return cols * L.nz;
+    }
     long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
     if (h->ns == 7)
         rbgs_kernel<7, false><<<nblk(threads, 256), 256, 0, h->stream>>>(L.a, L.b, L.x, g, col, 0, nullptr, 0, 0, 0.0);
