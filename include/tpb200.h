@@ -128,6 +128,12 @@ typedef struct {
                                  columns coloured by (i+j)&1, every column solved exactly by the Thomas algorithm; z is
                                  then never coarsened while x or y can be) - what thin reservoir layers (Dz << Dx, Dy)
                                  need.  Default 1 in 3-D; 2-D grids always use 0 */
+    int mg_tile_sweeps;       /* the z-line smoother works on tiles of columns (8 x 3 for nz <= 85) that live in one thread
+                                 block's shared memory: Gauss-Seidel inside a tile, the columns around it frozen (block
+                                 Jacobi between tiles, as hypre's hybrid smoother is between processes).  A tile does this
+                                 many sweeps before the tiles exchange their rims (one kernel launch per exchange);
+                                 0 = all sweeps of a smoothing step on frozen rims (default: on the 60x220x85 SPE10
+                                 case it costs 8 % more Krylov iterations than 1 and a third less time per iteration) */
     /* second stage: block ILU(0) of the nf x nf block stencil in red-black ordering, one block per
      * rank as PETSc bjacobi+ilu (the slab couplings to other ranks are dropped).  The triangular solves read an
      * fp32 colour-separated copy of the factor (fp64 arithmetic): a fixed preconditioner, converged fields are

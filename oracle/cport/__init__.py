@@ -53,7 +53,7 @@ class SolverOpts(C.Structure):
                 ("mg_pre", C.c_int), ("mg_post", C.c_int), ("mg_coarse_sweeps", C.c_int),
                 ("mg_min_cells", C.c_int), ("mg_overcorrection", C.c_double), ("mg_cycles", C.c_int),
                 ("mg_semi_theta", C.c_double), ("mg_full_below", C.c_int), ("mg_dd_stop", C.c_double),
-                ("mg_coarse_scale", C.c_double), ("mg_smoother", C.c_int),
+                ("mg_coarse_scale", C.c_double), ("mg_smoother", C.c_int), ("mg_tile_sweeps", C.c_int),
                 ("verbose", C.c_int)]
 
 
@@ -135,6 +135,7 @@ def default_opts(nphase):
     o.mg_dd_stop = 0.1
     o.mg_coarse_scale = 0.5
     o.mg_smoother = 1
+    o.mg_tile_sweeps = 0
     o.verbose = 0
     return o
 

@@ -60,6 +60,8 @@ typedef struct {
     int cx, cy, cz; /* coarsening factors towards the next level */
     double* a;
     double *x, *b, *r;
+    double* xt;          /* line-smoothed levels: the iterate between pre- and post-smoothing (smoothing is out of place) */
+    double *xs0, *xs1;   /* ... and two work vectors for the groups of sweeps in between */
     int line;            /* smoothed by zebra z-line Gauss-Seidel (tpb_solver_opts.mg_smoother) */
     double *lid, *llf, *lcp; /* Thomas factors of every column: 1/pivot, lower * 1/pivot, upper * 1/pivot */
 } mglevel;
@@ -552,6 +554,10 @@ static void mg_free(mghier* m) {
         free(m->lev[l].x);
         free(m->lev[l].b);
         free(m->lev[l].r);
+        free(m->lev[l].xt);
+        free(m->lev[l].xs0);
+        free(m->lev[l].xs1);
+        m->lev[l].xt = m->lev[l].xs0 = m->lev[l].xs1 = NULL;
         free(m->lev[l].lid);
         free(m->lev[l].llf);
         free(m->lev[l].lcp);
@@ -657,6 +663,9 @@ static void mg_setup(const tpc_handle_s* h, mghier* m, double* a0) {
         L->r = (double*)calloc(L->n, sizeof(double));
         L->cx = L->cy = L->cz = 1;
         L->line = line;
+        L->xt = line ? (double*)calloc(L->n, sizeof(double)) : NULL;
+        L->xs0 = line ? (double*)calloc(L->n, sizeof(double)) : NULL;
+        L->xs1 = line ? (double*)calloc(L->n, sizeof(double)) : NULL;
         L->lid = L->llf = L->lcp = NULL;
         if (line) mg_line_factors(L);
         if (line && L->nx == 1 && L->ny == 1) { /* a single column: the line solve is exact */
@@ -744,46 +753,101 @@ static void mg_rbgs(const mglevel* L, int ns, const double* b, double* x, int ze
     }
 }
 
-/* zebra z-line Gauss-Seidel: columns coloured by (i+j)&1, every column of a colour solved exactly by the Thomas
- * algorithm with the factors of mg_line_factors (same arithmetic as csrc/tpb_pc.cu zline kernels):
- *   d_k = rhs_k * id_k - lf_k * d_{k-1} ;  x_k = d_k - cp_k * x_{k+1}
- * rhs_k = b_k - sum over the four lateral neighbours (x-, x+, y-, y+; the other colour) */
-static void mg_zline(const mglevel* L, const double* b, double* x, int zero_guess) {
+/* Tile shape of the line smoother (csrc/tpb_pc.cu line_tile_shape): as many columns as give at most 2048 cells */
+static void line_tile_shape(int nz, int* tx, int* ty) {
+    static const int menu[3][2] = {{8, 3}, {4, 2}, {1, 1}};
+    const int cols_max = nz > 0 ? 2048 / nz : 1;
+    for (int q = 0; q < 3; q++)
+        if (menu[q][0] * menu[q][1] <= cols_max || q == 2) {
+            *tx = menu[q][0];
+            *ty = menu[q][1];
+            return;
+        }
+}
+
+/* Hybrid zebra z-line Gauss-Seidel (csrc/tpb_pc.cu line_smooth_kernel): the xy-plane is cut into tiles of tx x ty
+ * columns aligned at multiples of the tile shape; every tile does `nsweeps` zebra sweeps on its own (columns coloured
+ * by the global (i+j)&1, colour 0 first, every column solved exactly with the factors of mg_line_factors:
+ *   d_k = rhs_k * id_k - lf_k * d_{k-1} ;  x_k = d_k - cp_k * x_{k+1},
+ *   rhs_k = b_k - sum over the four lateral neighbours) while the columns outside the tile keep their values of
+ * entry - Gauss-Seidel inside a tile, block Jacobi between tiles, what hypre's hybrid smoother is between processes.
+ * On the GPU a tile lives in one thread block's shared memory for all its sweeps.  Out of place: xin (NULL = zero
+ * guess) is read, xout written. */
+static void mg_line_smooth1(const mglevel* L, const double* b, const double* xin, double* xout, int nsweeps) {
     const int nx = L->nx, ny = L->ny, nz = L->nz;
     const long n = L->n, np = (long)nx * ny;
-    for (int col = 0; col < 2; col++) {
-#pragma omp parallel for schedule(static)
-        for (long q = 0; q < np; q++) {
-            int i = (int)(q % nx), j = (int)(q / nx);
-            if (((i + j) & 1) != col) continue;
-            double dprev = 0.0;
-            for (int k = 0; k < nz; k++) {
-                long c = q + np * k;
-                double rhs = b[c];
-                if (!(zero_guess && col == 0)) {
-                    for (int s = 1; s < 5; s++) {
-                        long nb = nbr(nx, ny, nz, i, j, k, s);
-                        if (nb >= 0) rhs -= L->a[(long)s * n + c] * x[nb];
-                    }
+    int tx, ty;
+    line_tile_shape(nz, &tx, &ty);
+    const int ntx = (nx + tx - 1) / tx, nty = (ny + ty - 1) / ty;
+    const int hx = tx + 2, hy = ty + 2;
+#pragma omp parallel
+    {
+        double* xl = (double*)malloc(sizeof(double) * hx * hy * nz); /* tile + halo ring, [jj][ii][k] */
+#pragma omp for schedule(static)
+        for (int tile = 0; tile < ntx * nty; tile++) {
+            const int i0 = (tile % ntx) * tx, j0 = (tile / ntx) * ty;
+            for (int jj = 0; jj < hy; jj++)
+                for (int ii = 0; ii < hx; ii++) {
+                    const int i = i0 + ii - 1, j = j0 + jj - 1;
+                    double* col = xl + ((long)jj * hx + ii) * nz;
+                    const int in = xin && i >= 0 && i < nx && j >= 0 && j < ny;
+                    for (int k = 0; k < nz; k++) col[k] = in ? xin[i + (long)nx * j + np * k] : 0.0;
                 }
-                dprev = rhs * L->lid[c] - L->llf[c] * dprev;
-                x[c] = dprev;
-            }
-            double xn = 0.0;
-            for (int k = nz - 1; k >= 0; k--) {
-                long c = q + np * k;
-                xn = x[c] - L->lcp[c] * xn;
-                x[c] = xn;
-            }
+            for (int sw = 0; sw < nsweeps; sw++)
+                for (int colr = 0; colr < 2; colr++)
+                    for (int jj = 1; jj <= ty; jj++)
+                        for (int ii = 1; ii <= tx; ii++) {
+                            const int i = i0 + ii - 1, j = j0 + jj - 1;
+                            if (i >= nx || j >= ny || ((i + j) & 1) != colr) continue;
+                            double* me = xl + ((long)jj * hx + ii) * nz;
+                            const double* xm = me - nz, *xp = me + nz, *ym = me - (long)hx * nz, *yp = me + (long)hx * nz;
+                            const long q = i + (long)nx * j;
+                            double dprev = 0.0;
+                            for (int k = 0; k < nz; k++) {
+                                const long c = q + np * k;
+                                double rhs = b[c];
+                                if (i > 0) rhs -= L->a[1 * n + c] * xm[k];
+                                if (i < nx - 1) rhs -= L->a[2 * n + c] * xp[k];
+                                if (j > 0) rhs -= L->a[3 * n + c] * ym[k];
+                                if (j < ny - 1) rhs -= L->a[4 * n + c] * yp[k];
+                                dprev = rhs * L->lid[c] - L->llf[c] * dprev;
+                                me[k] = dprev;
+                            }
+                            double xn = 0.0;
+                            for (int k = nz - 1; k >= 0; k--) {
+                                xn = me[k] - L->lcp[q + np * k] * xn;
+                                me[k] = xn;
+                            }
+                        }
+            for (int jj = 1; jj <= ty; jj++)
+                for (int ii = 1; ii <= tx; ii++) {
+                    const int i = i0 + ii - 1, j = j0 + jj - 1;
+                    if (i >= nx || j >= ny) continue;
+                    const double* me = xl + ((long)jj * hx + ii) * nz;
+                    for (int k = 0; k < nz; k++) xout[i + (long)nx * j + np * k] = me[k];
+                }
         }
+        free(xl);
     }
 }
 
-static void mg_smooth(const mglevel* L, int ns, const double* b, double* x, int zero_guess) {
-    if (L->line)
-        mg_zline(L, b, x, zero_guess);
-    else
-        mg_rbgs(L, ns, b, x, zero_guess);
+/* `nsweeps` sweeps in groups of `group` (tpb_solver_opts.mg_tile_sweeps; <= 0: all in one group): a tile exchanges
+ * its rim with the neighbouring tiles between groups.  xin (NULL = zero guess) is only read, the last group writes
+ * xout, the groups before it alternate between xout's partner buffers (o0, o1 are two work vectors distinct from xin
+ * and xout). */
+static void mg_line_smooth(const mglevel* L, const double* b, const double* xin, double* xout, int nsweeps, int group,
+                           double* o0, double* o1) {
+    if (group <= 0 || group > nsweeps) group = nsweeps;
+    const int ncalls = (nsweeps + group - 1) / group;
+    const double* in = xin;
+    int left = nsweeps;
+    for (int j = 0; j < ncalls; j++) {
+        double* out = (j == ncalls - 1) ? xout : (((ncalls - 1 - j) & 1) ? o0 : o1);
+        const int sw = left < group ? left : group;
+        mg_line_smooth1(L, b, in, out, sw);
+        left -= sw;
+        in = out;
+    }
 }
 
 static void mg_residual(const mglevel* L, int ns, const double* b, const double* x, double* r) {
@@ -811,10 +875,10 @@ static void mg_restrict(const mglevel* f, const mglevel* c, const double* r, dou
                 for (int di = 0; di < f->cx; di++) {
                     int i = I * f->cx + di, j = Jc * f->cy + dj, k = Kc * f->cz + dk;
                     if (i >= f->nx || j >= f->ny || k >= f->nz) continue;
-                    /* the pre-smoothing sweep ended on colour 1 (cells (i+j+k)&1, or columns (i+j)&1 of a line-smoothed
-                     * level): those rows were just solved, their residual is zero and is not summed
-                     * (csrc/tpb_pc.cu restrict_cell) */
-                    if (f->line ? ((i + j) & 1) : ((i + j + k) & 1)) continue;
+                    /* point smoother: the pre-smoothing sweep ended on colour 1, those rows were just solved, their
+                     * residual is zero and is not summed (csrc/tpb_pc.cu restrict_cell).  Line-smoothed levels sum
+                     * every row: the hybrid smoother's tiles freeze their surroundings, so no row is exactly solved */
+                    if (!f->line && ((i + j + k) & 1)) continue;
                     acc += r[i + (long)f->nx * (j + (long)f->ny * k)];
                 }
         bc[C] = acc;
@@ -836,18 +900,32 @@ static void mg_vcycle_level(const tpc_handle_s* h, mghier* m, int l) {
     mglevel* L = &m->lev[l];
     if (l == m->nlev - 1) {
         int sweeps = m->last_sweeps > 0 ? m->last_sweeps : (o->mg_coarse_sweeps > 0 ? o->mg_coarse_sweeps : 1);
-        for (int s = 0; s < sweeps; s++) mg_smooth(L, ns, L->b, L->x, s == 0);
+        if (L->line)
+            mg_line_smooth(L, L->b, NULL, L->x, sweeps, o->mg_tile_sweeps, L->xs0, L->xs1);
+        else
+            for (int s = 0; s < sweeps; s++) mg_rbgs(L, ns, L->b, L->x, s == 0);
         return;
     }
     int pre = o->mg_pre > 0 ? o->mg_pre : 1;
     const int post = o->mg_post;
-    for (int s = 0; s < pre; s++) mg_smooth(L, ns, L->b, L->x, s == 0);
-    mg_residual(L, ns, L->b, L->x, L->r);
+    double* cur = L->x; /* the iterate after pre-smoothing */
+    if (L->line) {
+        cur = L->xt;
+        mg_line_smooth(L, L->b, NULL, cur, pre, o->mg_tile_sweeps, L->xs0, L->xs1);
+    } else
+        for (int s = 0; s < pre; s++) mg_rbgs(L, ns, L->b, L->x, s == 0);
+    mg_residual(L, ns, L->b, cur, L->r);
     mglevel* Cc = &m->lev[l + 1];
     mg_restrict(L, Cc, L->r, Cc->b);
     mg_vcycle_level(h, m, l + 1);
-    mg_prolong_add(L, Cc, Cc->x, L->x, o->mg_overcorrection);
-    for (int s = 0; s < post; s++) mg_smooth(L, ns, L->b, L->x, 0);
+    mg_prolong_add(L, Cc, Cc->x, cur, o->mg_overcorrection);
+    if (L->line) {
+        if (post > 0)
+            mg_line_smooth(L, L->b, cur, L->x, post, o->mg_tile_sweeps, L->xs0, L->xs1);
+        else
+            memcpy(L->x, cur, sizeof(double) * L->n);
+    } else
+        for (int s = 0; s < post; s++) mg_rbgs(L, ns, L->b, L->x, 0);
 }
 
 /* y = V(b): mg_cycles V-cycles from a zero initial guess */

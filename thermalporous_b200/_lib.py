@@ -43,7 +43,7 @@ class SolverOpts(C.Structure):
                 ("mg_pre", C.c_int), ("mg_post", C.c_int), ("mg_coarse_sweeps", C.c_int),
                 ("mg_min_cells", C.c_int), ("mg_overcorrection", C.c_double), ("mg_cycles", C.c_int),
                 ("mg_semi_theta", C.c_double), ("mg_full_below", C.c_int), ("mg_dd_stop", C.c_double),
-                ("mg_coarse_scale", C.c_double), ("mg_smoother", C.c_int),
+                ("mg_coarse_scale", C.c_double), ("mg_smoother", C.c_int), ("mg_tile_sweeps", C.c_int),
                 ("verbose", C.c_int)]
 
 

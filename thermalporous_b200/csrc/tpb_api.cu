@@ -328,6 +328,7 @@ int tpb_solver_defaults(int nphase, tpb_solver_opts* o) {
     o->mg_dd_stop = 0.1;
     o->mg_coarse_scale = 0.5;
     o->mg_smoother = TPB_MG_ZLINE;
+    o->mg_tile_sweeps = 0;
     o->verbose = 0;
     return TPB_OK;
 }

@@ -41,9 +41,12 @@ struct MgLevel {
     double* b = nullptr;  // multi-rank hierarchy) this rank's section of the gathered level
     double* x_own = nullptr;
     double* b_own = nullptr;
-    bool line = false;    // smoothed by zebra z-line Gauss-Seidel
-    double* fac = nullptr;   // 3 * cap: Thomas factors of every column (1/pivot | lower/pivot | upper/pivot)
-    long long fac_cap = 0;
+    bool line = false;    // smoothed by the hybrid zebra z-line Gauss-Seidel
+    double* fac = nullptr;   // 6 * cap: Thomas factors of every column (1/pivot | lower/pivot | upper/pivot), then the
+    long long fac_cap = 0;   // iterate between pre- and post-smoothing and two work vectors (xt, xs0, xs1 below)
+    double* xt() const { return fac + 3 * fac_cap; }
+    double* xs0() const { return fac + 4 * fac_cap; }
+    double* xs1() const { return fac + 5 * fac_cap; }
 };
 
 // Multi-rank slabs (K7 over NCCL): every rank coarsens its own slab with globally agreed coarsening factors
@@ -112,6 +115,7 @@ struct PcState {
     int64_t cap_l0 = 0;
     double *gx = nullptr, *gy = nullptr;
     bool graph_ok = false;
+    std::vector<long long> graph_sig;   // what the captured application depends on (level shapes, buffers, sweep counts)
 };
 
 namespace {
@@ -565,27 +569,36 @@ __global__ void __launch_bounds__(128) line_factor_kernel(const double* __restri
     }
 }
 
-// One colour of a zebra sweep for a tile of `cpc` (<= 32) columns held in shared memory:
-//   phase A (all threads, one cell per trip): e = (b - sum over the four lateral neighbours) * id -> smem, and the
-//            factors lf, cp -> smem.  Every load is independent of the recurrences, blocks are large (up to 1024
-//            threads) so that a tile is one or two trips: the memory round trips of a pass overlap instead of queueing;
-//   phase B (one warp per column): both first-order recurrences d_k = e_k - lf_k d_{k-1} (up) and
-//            x_k = d_k - cp_k x_{k+1} (down) as warp scans over affine maps, 32 levels of the column per round with the
-//            carry broadcast from the last lane - 5 shuffle steps per round instead of a chain of nz dependent FMAs;
-//   phase C (all threads): x written back.
-// Shared layout: [column][k], column stride nzp = nz | 1 doubles (odd: phase A's column-fastest stores and phase B's
-// k-fastest loads are both free of bank conflicts).
-// Column slot t of the colour: j = t / nxh, i = 2 (t % nxh) + ((col + j) & 1), as the point smoother enumerates cells.
-// PROLONG / zero_guess as in rbgs_cell: a line update never reads its own column's old values, so the coarse
-// correction of the other colour's columns is formed on the fly.
-struct LineTile {
-    double *e, *lf, *cp;   // [cpc][nzp]
-    int nzp;
-};
+// Hybrid zebra z-line smoother.  The xy-plane is cut into tiles of tx x ty columns (8 x 3 while a tile holds at most
+// 2048 cells, i.e. nz <= 85); ONE thread block keeps a tile - its x values with a one-column rim, and the right-hand
+// sides, couplings and Thomas factors of its columns - in shared memory and does `nsw` complete zebra sweeps on it
+// (columns coloured by the global (i+j)&1, colour 0 first) while the rim stays frozen at its values of entry:
+// Gauss-Seidel inside a tile, block Jacobi between tiles, what hypre's hybrid smoother is between processes.
+// A smoothing step is one launch per group of mg_tile_sweeps sweeps (default: one launch) instead of two launches per
+// sweep, the operator is read once per launch, and everything between the first load and the last store runs out of
+// shared memory:
+//   load    couplings a1..a4 (zeroed where there is no neighbour), 1/pivot, lf, cp and b of the tile's cells; x of tile
+//           + rim (PROLONG: x + omega * xc[aggregate], the coarse correction never exists in memory; xin == nullptr:
+//           zero guess, no loads);
+//   pass    (2 per sweep) the cells of the pass's colour: e = (b - sum a_s x[lateral]) / pivot; then one warp per
+//           column of the colour: d_k = e_k - lf_k d_{k-1} up, x_k = d_k - cp_k x_{k+1} down, each as ONE warp scan
+//           over affine maps (a lane composes its 3 consecutive planes first);
+//   store   x of the tile -> xout (out of place: other tiles read xin concurrently).
+// Same arithmetic as oracle/cport mg_line_smooth1 up to the association order of the scans.
+// Measured (tools/bench_line.cu, B200): a block lives ~17 k cycles for one sweep, ~24 k for two, issue-bound (1.1 k
+// instructions per warp at 35 % issue utilisation), not memory-bound; 60x220x85: 57 / 71 us per launch.
+constexpr int LS_THREADS = 1024;
+constexpr int LS_CPT = 2;       // a tile holds at most LS_CPT * LS_THREADS cells (bounds its shared memory)
 __host__ __device__ __forceinline__ int line_nzp(int nz) { return nz | 1; }
-__device__ __forceinline__ LineTile line_tile(double* sm, int nz, int cpc) {
-    const int nzp = line_nzp(nz);
-    return LineTile{sm, sm + (size_t)nzp * cpc, sm + 2 * (size_t)nzp * cpc, nzp};
+__host__ __device__ inline void line_tile_shape(int nz, int& tx, int& ty) {
+    const int menu[3][2] = {{8, 3}, {4, 2}, {1, 1}};
+    const int cols_max = nz > 0 ? (LS_CPT * LS_THREADS) / nz : 1;
+    for (int q = 0; q < 3; q++)
+        if (menu[q][0] * menu[q][1] <= cols_max || q == 2) {
+            tx = menu[q][0];
+            ty = menu[q][1];
+            return;
+        }
 }
 
 // inclusive warp scan of the affine maps v -> M v + C (composition order: lower lanes first)
@@ -601,105 +614,236 @@ __device__ __forceinline__ void affine_scan(double& M, double& C, int lane) {
     }
 }
 
-template <bool PROLONG>
-__device__ __forceinline__ void line_tile_pass(const double* __restrict__ a, const double* __restrict__ fac,
-                                               const double* b, double* x, const LevGeom& g, int col, bool zero_guess,
-                                               const double* xc, int cnx, int cny, double omega, int q0, int cpc,
-                                               int lg2, const LineTile& T, int tid, int nth, bool static_first) {
-    const int nz = g.nz, nxh = (g.nx + 1) >> 1, ncol = nxh * g.ny;
-    const long long n = g.n, np = (long long)g.nx * g.ny;
-    const int tile = nz * cpc;
-    if (static_first) pdl_wait();
-    for (int idx = tid; idx < tile; idx += nth) {
-        const int k = idx / cpc, qq = idx - k * cpc, t = q0 + qq;
-        bool act = t < ncol;
-        int i = 0, j = 0;
-        if (act) {
-            j = t / nxh;
-            i = 2 * (t - j * nxh) + ((col + j) & 1);
-            act = i < g.nx;
-        }
-        double e = 0.0, lf = 0.0, cp = 0.0;
-        if (act) {
-            const long long c = i + (long long)g.nx * j + np * k;
-            lf = fac[n + c];
-            cp = fac[2 * n + c];
-            const double id = fac[c];
-            double rhs = b[c];
-            if (!zero_guess) {
-                double tt[4];
+// one column by one warp: ev holds e on entry and d in between; x -> xcol.  MM consecutive levels per lane; the
+// arrays are walked with strides `st` / `xst` doubles (odd: free of bank conflicts).
+template <int MM>
+__device__ __forceinline__ void line_column_solve(double* ev, const double* lv, const double* cv, double* xcol, int st,
+                                                  int xst, int nz, int lane) {
+    double m[MM], c[MM];
+    double Mc = 1.0, Cc = 0.0;
 #pragma unroll
-                for (int s = 1; s < 5; s++) {
-                    bool ex;
-                    const long long nb = nbr_clamped(g.nx, g.ny, g.nz, i, j, k, c, s, ex);
-                    double xv = x[nb];
-                    if (PROLONG) {
-                        const int d = ((s - 1) & 1) ? 1 : -1;
-                        const int ii = (ex && s < 3) ? i + d : i, jj = (ex && s >= 3) ? j + d : j;
-                        xv += omega * xc[(ii >> (g.cx - 1)) + (long long)cnx * ((jj >> (g.cy - 1)) + (long long)cny * (k >> (g.cz - 1)))];
-                    }
-                    const double p = a[(long long)s * n + c] * xv;
-                    tt[s - 1] = ex ? p : 0.0;
-                }
+    for (int u = 0; u < MM; u++) {                       // up: d_k = e_k - lf_k d_{k-1}
+        const int k = lane * MM + u;
+        m[u] = k < nz ? -lv[k * st] : 1.0;
+        c[u] = k < nz ? ev[k * st] : 0.0;
+        Cc = fma(m[u], Cc, c[u]);
+        Mc = Mc * m[u];
+    }
+    affine_scan(Mc, Cc, lane);
+    double d = __shfl_up_sync(0xffffffffu, Cc, 1);
+    if (lane == 0) d = 0.0;
 #pragma unroll
-                for (int s = 0; s < 4; s++) rhs -= tt[s];
-            }
-            e = rhs * id;
-        }
-        const int o = qq * T.nzp + k;
-        T.e[o] = e;
-        T.lf[o] = lf;
-        T.cp[o] = cp;
+    for (int u = 0; u < MM; u++) {
+        const int k = lane * MM + u;
+        d = fma(m[u], d, c[u]);
+        if (k < nz) ev[k * st] = d;
     }
-    __syncthreads();
-    {
-        const int lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
-        for (int qq = wid; qq < cpc; qq += nw) {
-            double* ev = T.e + qq * T.nzp;
-            const double* lv = T.lf + qq * T.nzp;
-            const double* cv = T.cp + qq * T.nzp;
-            double carry = 0.0;
-            for (int k0 = 0; k0 < nz; k0 += 32) {          // up: d_k = e_k - lf_k d_{k-1}
-                const int k = k0 + lane;
-                double M = k < nz ? -lv[k] : 1.0, C = k < nz ? ev[k] : 0.0;
-                affine_scan(M, C, lane);
-                const double d = fma(M, carry, C);
-                if (k < nz) ev[k] = d;
-                carry = __shfl_sync(0xffffffffu, d, 31);
-            }
-            __syncwarp();
-            carry = 0.0;
-            for (int r0 = 0; r0 < nz; r0 += 32) {          // down: x_k = d_k - cp_k x_{k+1}, walked as r = nz-1-k
-                const int k = nz - 1 - (r0 + lane);
-                double M = k >= 0 ? -cv[k] : 1.0, C = k >= 0 ? ev[k] : 0.0;
-                affine_scan(M, C, lane);
-                const double xk = fma(M, carry, C);
-                if (k >= 0) ev[k] = xk;
-                carry = __shfl_sync(0xffffffffu, xk, 31);
-            }
-        }
+    __syncwarp();
+    Mc = 1.0;
+    Cc = 0.0;
+#pragma unroll
+    for (int u = 0; u < MM; u++) {                       // down: x_k = d_k - cp_k x_{k+1}, walked as r = nz-1-k
+        const int k = nz - 1 - (lane * MM + u);
+        m[u] = k >= 0 ? -cv[k * st] : 1.0;
+        c[u] = k >= 0 ? ev[k * st] : 0.0;
+        Cc = fma(m[u], Cc, c[u]);
+        Mc = Mc * m[u];
     }
-    __syncthreads();
-    for (int idx = tid; idx < tile; idx += nth) {
-        const int k = idx / cpc, qq = idx - k * cpc, t = q0 + qq;
-        if (t < ncol) {
-            const int j = t / nxh, i = 2 * (t - j * nxh) + ((col + j) & 1);
-            if (i < g.nx) x[i + (long long)g.nx * j + np * k] = T.e[qq * T.nzp + k];
-        }
+    affine_scan(Mc, Cc, lane);
+    double xv = __shfl_up_sync(0xffffffffu, Cc, 1);
+    if (lane == 0) xv = 0.0;
+#pragma unroll
+    for (int u = 0; u < MM; u++) {
+        const int k = nz - 1 - (lane * MM + u);
+        xv = fma(m[u], xv, c[u]);
+        if (k >= 0) xcol[k * xst] = xv;
+    }
+}
+// any nz: 32 levels per round, the carry broadcast from the last lane (xcol has its own stride)
+__device__ __forceinline__ void line_column_solve_rounds(double* ev, const double* lv, const double* cv, double* xcol,
+                                                         int st, int xst, int nz, int lane) {
+    double carry = 0.0;
+    for (int k0 = 0; k0 < nz; k0 += 32) {
+        const int k = k0 + lane;
+        double M = k < nz ? -lv[k * st] : 1.0, C = k < nz ? ev[k * st] : 0.0;
+        affine_scan(M, C, lane);
+        const double d = fma(M, carry, C);
+        if (k < nz) ev[k * st] = d;
+        carry = __shfl_sync(0xffffffffu, d, 31);
+    }
+    __syncwarp();
+    carry = 0.0;
+    for (int r0 = 0; r0 < nz; r0 += 32) {
+        const int k = nz - 1 - (r0 + lane);
+        double M = k >= 0 ? -cv[k * st] : 1.0, C = k >= 0 ? ev[k * st] : 0.0;
+        affine_scan(M, C, lane);
+        const double xk = fma(M, carry, C);
+        if (k >= 0) xcol[k * xst] = xk;
+        carry = __shfl_sync(0xffffffffu, xk, 31);
     }
 }
 
-constexpr int ZL_THREADS = 1024;
+#ifdef TPB_LINE_TIMING   // tools/bench_line.cu: phase time stamps of block 0
+__device__ long long g_line_clk[8];
+#define LINE_STAMP(q) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_line_clk[q] = clock64(); } while (0)
+#else
+#define LINE_STAMP(q) do { } while (0)
+#endif
+// Shared layout: plane-major, [k][column] with the column count padded to an odd number - a warp walking the columns of
+// one plane (load, right-hand-side and store phases) and a warp walking the planes of one column (solve phase) are
+// both free of bank conflicts.
+struct LineSmem {
+    double *xs;                                    // [nz][HP]  iterate of tile + rim, HP = (TX+2)*(TY+2) | 1
+    double *e, *lf, *cp, *a1, *a2, *a3, *a4, *id, *bb;   // [nz][CP] each, CP = TX*TY | 1
+};
+__host__ __device__ __forceinline__ int line_cp(int tx, int ty) { return (tx * ty) | 1; }
+__host__ __device__ __forceinline__ int line_hp(int tx, int ty) { return ((tx + 2) * (ty + 2)) | 1; }
+__host__ __device__ inline size_t line_smem_doubles(int nz, int tx, int ty) {
+    return (size_t)nz * (line_hp(tx, ty) + 9 * line_cp(tx, ty));
+}
+__device__ __forceinline__ LineSmem line_smem_of(double* sm, int nz, int tx, int ty) {
+    const size_t halo = (size_t)nz * line_hp(tx, ty), t = (size_t)nz * line_cp(tx, ty);
+    double* q = sm + halo;
+    return LineSmem{sm, q, q + t, q + 2 * t, q + 3 * t, q + 4 * t, q + 5 * t, q + 6 * t, q + 7 * t, q + 8 * t};
+}
+
+// All sweeps of one TX x TY tile by one thread block (tid, nth: thread index and count inside the block, nth a
+// multiple of 32).  Nothing is kept in registers between the phases - couplings, factors and right-hand sides of the
+// tile live in shared memory next to the iterate - so the kernel runs without spills at 1024 threads per block, and
+// every phase is a short grid-stride loop over the tile's cells (the right-hand-side phase over the cells of the
+// pass's colour only: all lanes busy).  TX is a power of two and both are compile-time constants, so decoding a cell
+// costs shifts and a constant division; the rim of the tile is loaded by the threads of the tile's edge columns.
+// 32-bit cell indices (a slab holds fewer than 2^31 cells).  Cells of the tile that lie outside the box get zero
+// couplings and a zero 1/pivot: they stay 0 and need no tests in the passes.
+template <bool PROLONG, int TX, int TY>
+__device__ __forceinline__ void line_tile_smooth(const double* __restrict__ a, const double* __restrict__ fac,
+                                                 const double* b, const double* xin, double* xout, const LevGeom& g,
+                                                 const double* xc, int cnx, int cny, double omega, int nsw, int i0, int j0,
+                                                 double* sm, int tid, int nth, bool wait_first) {
+    constexpr int HX = TX + 2, CP = (TX * TY) | 1, HP = ((TX + 2) * (TY + 2)) | 1;
+    constexpr int TXH = TX > 1 ? TX / 2 : 1;   // columns of one colour per tile row
+    const int nz = g.nz, nx = g.nx, ny = g.ny;
+    const int np = nx * ny;
+    const long long n = g.n;
+    const LineSmem S = line_smem_of(sm, nz, TX, TY);
+    const int cells = TX * TY * nz;
+    LINE_STAMP(0);
+    // ---- set-up products of the tile (may be loaded before the predecessor kernel is done)
+#pragma unroll 2
+    for (int idx = tid; idx < cells; idx += nth) {
+        const int ii = idx & (TX - 1), r = idx / TX, jj = r % TY, k = r / TY;
+        const int i = i0 + ii, j = j0 + jj;
+        const bool in = i < nx && j < ny;
+        const int c = i + nx * j + np * k;
+        const int o = k * CP + jj * TX + ii;
+        S.a1[o] = (in && i > 0) ? a[n + c] : 0.0;
+        S.a2[o] = (in && i < nx - 1) ? a[2 * n + c] : 0.0;
+        S.a3[o] = (in && j > 0) ? a[3 * n + c] : 0.0;
+        S.a4[o] = (in && j < ny - 1) ? a[4 * n + c] : 0.0;
+        S.id[o] = in ? fac[c] : 0.0;
+        S.lf[o] = in ? fac[n + c] : 0.0;
+        S.cp[o] = in ? fac[2 * n + c] : 0.0;
+    }
+    LINE_STAMP(1);
+    if (wait_first) pdl_wait();
+    // ---- right-hand sides; x of the tile (own cells) and of its rim (edge columns' threads)
+#pragma unroll 2
+    for (int idx = tid; idx < cells; idx += nth) {
+        const int ii = idx & (TX - 1), r = idx / TX, jj = r % TY, k = r / TY;
+        const int i = i0 + ii, j = j0 + jj;
+        const bool in = i < nx && j < ny;
+        const int c = i + nx * j + np * k;
+        const int so = k * HP + (jj + 1) * HX + (ii + 1);
+        S.bb[k * CP + jj * TX + ii] = in ? b[c] : 0.0;
+        auto xval = [&](int ci, int cj, int cc) -> double {   // input iterate at cell (ci, cj, k), 0 outside the box
+            if (xin == nullptr || ci < 0 || ci >= nx || cj < 0 || cj >= ny) return 0.0;
+            double v = xin[cc];
+            if (PROLONG) v += omega * xc[(ci >> (g.cx - 1)) + cnx * ((cj >> (g.cy - 1)) + cny * k)];
+            return v;
+        };
+        S.xs[so] = xval(i, j, c);
+        if (ii == 0) S.xs[so - 1] = xval(i - 1, j, c - 1);
+        if (ii == TX - 1) S.xs[so + 1] = xval(i + 1, j, c + 1);
+        if (jj == 0) S.xs[so - HX] = xval(i, j - 1, c - nx);
+        if (jj == TY - 1) S.xs[so + HX] = xval(i, j + 1, c + nx);
+    }
+    __syncthreads();
+    LINE_STAMP(2);
+    const int lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
+    const int mm = (nz + 31) / 32;
+    const int par0 = (i0 + j0) & 1;
+    for (int sw = 0; sw < nsw; sw++) {
+        for (int col = 0; col < 2; col++) {
+            // cells of this colour: ih-th column of the colour in tile row jj
+            for (int idx = tid; idx < TXH * TY * nz; idx += nth) {
+                const int ih = idx & (TXH - 1), r = idx / TXH, jj = r % TY, k = r / TY;
+                const int ii = TX > 1 ? 2 * ih + ((par0 + jj + col) & 1) : 0;
+                if (TX == 1 && ((par0 + jj) & 1) != col) continue;
+                const int o = k * CP + jj * TX + ii;
+                const double* xs = S.xs + k * HP + (jj + 1) * HX + (ii + 1);
+                double rhs = S.bb[o];
+                rhs = fma(-S.a1[o], xs[-1], rhs);
+                rhs = fma(-S.a2[o], xs[1], rhs);
+                rhs = fma(-S.a3[o], xs[-HX], rhs);
+                rhs = fma(-S.a4[o], xs[HX], rhs);
+                S.e[o] = rhs * S.id[o];
+            }
+            __syncthreads();
+            if (sw == 0 && col == 0) LINE_STAMP(3);
+            for (int q = wid; q < TX * TY; q += nw) {
+                const int ii = q & (TX - 1), jj = q / TX;
+                if (((par0 + ii + jj) & 1) != col) continue;
+                double* ev = S.e + q;
+                const double* lv = S.lf + q;
+                const double* cv = S.cp + q;
+                double* xcol = S.xs + (jj + 1) * HX + (ii + 1);
+                if (mm <= 3)
+                    line_column_solve<3>(ev, lv, cv, xcol, CP, HP, nz, lane);
+                else if (mm <= 7)
+                    line_column_solve<7>(ev, lv, cv, xcol, CP, HP, nz, lane);
+                else
+                    line_column_solve_rounds(ev, lv, cv, xcol, CP, HP, nz, lane);
+            }
+            __syncthreads();
+            if (sw == 0 && col == 0) LINE_STAMP(4);
+        }
+    }
+    LINE_STAMP(5);
+#pragma unroll 2
+    for (int idx = tid; idx < cells; idx += nth) {
+        const int ii = idx & (TX - 1), r = idx / TX, jj = r % TY, k = r / TY;
+        const int i = i0 + ii, j = j0 + jj;
+        if (i < nx && j < ny) xout[i + nx * j + np * k] = S.xs[k * HP + (jj + 1) * HX + (ii + 1)];
+    }
+    LINE_STAMP(6);
+}
+
+// run-time tile shape -> compile-time instantiation (the shapes of line_tile_shape)
 template <bool PROLONG>
-__global__ void __launch_bounds__(ZL_THREADS) zline_kernel(const double* __restrict__ a, const double* __restrict__ fac,
-                                                           const double* b, double* x, LevGeom g, int col, int zero_guess,
-                                                           const double* xc, int cnx, int cny, double omega, int cpc,
-                                                           int lg2) {
-    extern __shared__ double zl_sm[];
+__device__ __forceinline__ void line_tile_smooth_any(int tx, int ty, const double* __restrict__ a,
+                                                     const double* __restrict__ fac, const double* b, const double* xin,
+                                                     double* xout, const LevGeom& g, const double* xc, int cnx, int cny,
+                                                     double omega, int nsw, int i0, int j0, double* sm, int tid, int nth,
+                                                     bool wait_first) {
+    if (tx == 8 && ty == 3)
+        line_tile_smooth<PROLONG, 8, 3>(a, fac, b, xin, xout, g, xc, cnx, cny, omega, nsw, i0, j0, sm, tid, nth, wait_first);
+    else if (tx == 4 && ty == 2)
+        line_tile_smooth<PROLONG, 4, 2>(a, fac, b, xin, xout, g, xc, cnx, cny, omega, nsw, i0, j0, sm, tid, nth, wait_first);
+    else
+        line_tile_smooth<PROLONG, 1, 1>(a, fac, b, xin, xout, g, xc, cnx, cny, omega, nsw, i0, j0, sm, tid, nth, wait_first);
+}
+
+template <bool PROLONG>
+__global__ void __launch_bounds__(LS_THREADS) line_smooth_kernel(const double* __restrict__ a, const double* __restrict__ fac,
+                                                                 const double* b, const double* xin, double* xout,
+                                                                 LevGeom g, const double* xc, int cnx, int cny, double omega,
+                                                                 int nsw, int tx, int ty) {
+    extern __shared__ double ls_sm[];
     pdl_launch_dependents();
-    const LineTile T = line_tile(zl_sm, g.nz, cpc);
-    line_tile_pass<PROLONG>(a, fac, b, x, g, col, zero_guess != 0, xc, cnx, cny, omega, (int)blockIdx.x * cpc, cpc, lg2, T,
-                            (int)threadIdx.x, (int)blockDim.x, true);
+    const int ntx = (g.nx + tx - 1) / tx;
+    const int i0 = ((int)blockIdx.x % ntx) * tx, j0 = ((int)blockIdx.x / ntx) * ty;
+    line_tile_smooth_any<PROLONG>(tx, ty, a, fac, b, xin, xout, g, xc, cnx, cny, omega, nsw, i0, j0, ls_sm, (int)threadIdx.x,
+                                  (int)blockDim.x, true);
 }
 
 // one colour of a red-black Gauss-Seidel sweep: colour = (i+j+k)&1.  Threads walk the cells of the
@@ -791,9 +935,9 @@ __global__ void __launch_bounds__(256) rbgs_kernel(const double* __restrict__ a,
 // bc[C] = sum over the aggregate of (b - A x)  (residual + restriction fused).  The aggregate is walked as a
 // fully unrolled 2x2x2 box; the summation order (k, j, i; within a cell diag, x-, x+, ...) is the one the CPU
 // restatement uses.
-// Only the cells of colour 0 contribute: the restriction always follows a pre-smoothing sweep whose last pass
-// updated colour 1 (cells with (i+j+k)&1, or whole columns with (i+j)&1 on a line-smoothed level), and a
-// Gauss-Seidel update leaves a zero residual in the rows it solved - half of the loads.
+// Point-smoothed levels: only the cells of colour 0 contribute - the restriction always follows a pre-smoothing sweep
+// whose last pass updated colour 1, and a Gauss-Seidel update leaves a zero residual in the rows it solved (half of the
+// loads).  Line-smoothed levels sum every row: the hybrid smoother's tiles freeze their rims, no row is exactly solved.
 template <int NS>
 __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, const double* b, const double* x,
                                                 const LevGeom& f, int I, int Jc, int Kc) {
@@ -803,7 +947,7 @@ __device__ __forceinline__ double restrict_cell(const double* __restrict__ a, co
         const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
         const int i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
         const bool ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz &&
-                        ((i + j + (f.line ? 0 : k)) & 1) == 0;
+                        (f.line || ((i + j + k) & 1) == 0);
         r[q] = 0.0;
         if (ok) {
             long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
@@ -841,7 +985,7 @@ __global__ void __launch_bounds__(256) restrict_kernel(const double* __restrict_
         tpb_ijk(C, cg.nx, cg.ny, I, Jc, Kc);
         const int di = q & 1, dj = (q >> 1) & 1, dk = q >> 2;
         i = I * f.cx + di, j = Jc * f.cy + dj, k = Kc * f.cz + dk;
-        ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && ((i + j + (f.line ? 0 : k)) & 1) == 0;
+        ok = di < f.cx && dj < f.cy && dk < f.cz && i < f.nx && j < f.ny && k < f.nz && (f.line || ((i + j + k) & 1) == 0);
     }
     pdl_launch_dependents();
     const long long c = ok ? i + (long long)f.nx * (j + (long long)f.ny * k) : 0;
@@ -869,14 +1013,56 @@ __global__ void __launch_bounds__(256) restrict_kernel(const double* __restrict_
     if (q == 0 && C < cg.n) bc[C] = sum;
 }
 
+// Line-smoothed levels (z never coarsened, every row contributes): one thread per coarse cell walks its <= 2 x 2 fine
+// cells; the two x-neighbours share their sectors inside the thread, so the big levels run at memory speed with a
+// quarter of the threads of the 8-lane kernel above.  Summation order as restrict_cell (j, then i).
+__global__ void __launch_bounds__(256) restrict_line_kernel(const double* __restrict__ a, const double* b, const double* x,
+                                                            LevGeom f, LevGeom cg, double* __restrict__ bc) {
+    const long long C = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    int I = 0, Jc = 0, k = 0;
+    const bool on = C < cg.n;
+    if (on) tpb_ijk(C, cg.nx, cg.ny, I, Jc, k);
+    double aa[4][7];
+    bool ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int di = q & 1, dj = q >> 1;
+        const int i = I * f.cx + di, j = Jc * f.cy + dj;
+        ok[q] = on && di < f.cx && dj < f.cy && i < f.nx && j < f.ny;
+        const long long c = ok[q] ? i + (long long)f.nx * (j + (long long)f.ny * k) : 0;
+#pragma unroll
+        for (int s = 0; s < 7; s++) aa[q][s] = ok[q] ? a[(long long)s * f.n + c] : 0.0;   // set-up data: before the wait
+    }
+    pdl_wait();
+    double sum = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (!ok[q]) continue;
+        const int di = q & 1, dj = q >> 1;
+        const int i = I * f.cx + di, j = Jc * f.cy + dj;
+        const long long c = i + (long long)f.nx * (j + (long long)f.ny * k);
+        double acc = b[c] - aa[q][0] * x[c];
+#pragma unroll
+        for (int s = 1; s < 7; s++) {
+            bool ex;
+            const long long nb = nbr_clamped(f.nx, f.ny, f.nz, i, j, k, c, s, ex);
+            const double p = aa[q][s] * x[nb];
+            acc -= ex ? p : 0.0;
+        }
+        sum += acc;
+    }
+    if (on) bc[C] = sum;
+}
+
 __global__ void __launch_bounds__(256) prolong_add_kernel(const double* __restrict__ xc, LevGeom f, LevGeom cg,
-                                                          double omega, double* __restrict__ x) {
+                                                          double omega, const double* xin, double* x) {
     long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= f.n) return;
     int i, j, k;
     tpb_ijk(c, f.nx, f.ny, i, j, k);
     long long C = (i >> (f.cx - 1)) + (long long)cg.nx * ((j >> (f.cy - 1)) + (long long)cg.ny * (k >> (f.cz - 1)));
-    x[c] += omega * xc[C];
+    x[c] = xin[c] + omega * xc[C];   // (xin == x on point-smoothed levels, the iterate after pre-smoothing otherwise)
 }
 
 // residual only (used between V-cycles when mg_cycles > 1): r = b - A x
@@ -904,50 +1090,66 @@ struct TailLevel {
     const double* a;
     double* x;
     double* b;
-    const double* fac;   // line-smoothed levels: Thomas factors
-    int cpc, lg2;        // columns per shared-memory tile (power of two) and its log2
+    const double* fac;      // line-smoothed levels: Thomas factors,
+    double *xt, *xs0, *xs1; // the iterate between pre- and post-smoothing and two work vectors (smoothing is out of place)
+    int tx, ty;             // tile shape
 };
 struct TailArgs {
     int nlev;
     TailLevel lev[MAXLEV];
-    int pre, post, coarse_sweeps;
+    int pre, post, coarse_sweeps, tile_sweeps;
     double omega;
 };
 
-// The sub-V-cycle over a run of levels inside one kernel; the barrier between colour passes is a template
-// parameter.  Measured on B200 (60x220x85, r1): sharing the levels of <= 160 k cells among a co-resident
-// cooperative grid (grid.sync) was no faster than one launch per pass replayed from a CUDA graph, and one
-// 8-CTA thread-block cluster (cluster.sync) was 12 % slower (too little memory-level parallelism), so only the
-// single-CTA tail (levels <= TAIL_CELLS, __syncthreads) is kept.  Level vectors b, x are written and re-read
-// inside the same kernel, so they are plain pointers here (no __restrict__/read-only path).
+// The sub-V-cycle over a run of levels inside one kernel; the barrier between passes is a template parameter.
+// Measured on B200 (60x220x85, r1): sharing the levels of <= 160 k cells among a co-resident cooperative grid
+// (grid.sync) was no faster than one launch per pass replayed from a CUDA graph, and one 8-CTA thread-block cluster
+// (cluster.sync) was 12 % slower (too little memory-level parallelism); r2 tried a counter barrier over a co-resident
+// grid for the line smoother's passes: no faster either (a grid-wide barrier costs what a dependent launch costs).
+// So only the single-CTA tail (levels <= TAIL_CELLS, __syncthreads) is kept.  Level vectors b, x are written and
+// re-read inside the same kernel, so they are plain pointers here (no __restrict__/read-only path).
 struct BlockBarrier {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
 extern __shared__ double tail_sm[];
 
+// `nsw` sweeps of the hybrid line smoother on a whole level by one block: groups of tile_sweeps sweeps, the tiles of a
+// group one after the other (out of place, so the order does not matter); same buffer rotation as oracle/cport
+// mg_line_smooth.  xin == nullptr: zero guess; PROLONG: xin + omega * P xc is what the first group reads.
+template <bool PROLONG, class Barrier>
+__device__ __forceinline__ void cyc_line_smooth(const TailLevel& L, const double* xin, double* xout, int nsw, int group,
+                                                const double* xc, int cnx, int cny, double omega, Barrier& bar) {
+    const LevGeom& g = L.g;
+    if (group <= 0 || group > nsw) group = nsw;
+    const int ncalls = (nsw + group - 1) / group;
+    const int ntx = (g.nx + L.tx - 1) / L.tx, nty = (g.ny + L.ty - 1) / L.ty;
+    const double* in = xin;
+    int left = nsw;
+    for (int c = 0; c < ncalls; c++) {
+        double* out = (c == ncalls - 1) ? xout : (((ncalls - 1 - c) & 1) ? L.xs0 : L.xs1);
+        const int sw = left < group ? left : group;
+        for (int t = 0; t < ntx * nty; t++) {
+            const int i0 = (t % ntx) * L.tx, j0 = (t / ntx) * L.ty;
+            if (PROLONG && c == 0)
+                line_tile_smooth_any<true>(L.tx, L.ty, L.a, L.fac, L.b, in, out, g, xc, cnx, cny, omega, sw, i0, j0, tail_sm,
+                                           (int)threadIdx.x, (int)blockDim.x, false);
+            else
+                line_tile_smooth_any<false>(L.tx, L.ty, L.a, L.fac, L.b, in, out, g, nullptr, 0, 0, 0.0, sw, i0, j0, tail_sm,
+                                            (int)threadIdx.x, (int)blockDim.x, false);
+            __syncthreads();   // the tile's shared memory is reused by the next one
+        }
+        bar();
+        left -= sw;
+        in = out;
+    }
+}
+
 template <int NS, bool PROLONG, class Barrier>
 __device__ __forceinline__ void cyc_sweep(const TailLevel& L, bool zero_guess, const double* xc, int cnx, int cny,
                                           double omega, long long tid, long long nth, Barrier& bar) {
     const LevGeom& g = L.g;
     const int nxh = (g.nx + 1) >> 1;
-    if (NS == 7 && g.line) {
-        // zebra z-line sweep: the colour's columns in tiles of L.cpc through the block's shared memory
-        const int ncol = nxh * g.ny;
-        const LineTile T = line_tile(tail_sm, g.nz, L.cpc);
-        for (int col = 0; col < 2; col++) {
-            for (int q0 = 0; q0 < ncol; q0 += L.cpc) {
-                if (PROLONG && col == 0)
-                    line_tile_pass<true>(L.a, L.fac, L.b, L.x, g, col, false, xc, cnx, cny, omega, q0, L.cpc, L.lg2, T, (int)tid,
-                                         (int)nth, false);
-                else
-                    line_tile_pass<false>(L.a, L.fac, L.b, L.x, g, col, zero_guess && col == 0, nullptr, 0, 0, 0.0, q0, L.cpc,
-                                          L.lg2, T, (int)tid, (int)nth, false);
-                bar();
-            }
-        }
-        return;
-    }
     const long long total = (long long)g.ny * g.nz * nxh;
     for (int col = 0; col < 2; col++) {
         for (long long t = tid; t < total; t += nth) {
@@ -970,12 +1172,17 @@ template <int NS, class Barrier>
 __device__ __forceinline__ void cyc_down(const TailArgs& A, int l0, int l1, long long tid, long long nth, Barrier& bar) {
     for (int l = l0; l < l1; l++) {
         const TailLevel& L = A.lev[l];
-        for (int s = 0; s < A.pre; s++) cyc_sweep<NS, false>(L, s == 0, nullptr, 0, 0, 0.0, tid, nth, bar);
+        const bool line = NS == 7 && L.g.line;
+        if (line)
+            cyc_line_smooth<false>(L, nullptr, L.xt, A.pre, A.tile_sweeps, nullptr, 0, 0, 0.0, bar);
+        else
+            for (int s = 0; s < A.pre; s++) cyc_sweep<NS, false>(L, s == 0, nullptr, 0, 0, 0.0, tid, nth, bar);
+        const double* cur = line ? L.xt : L.x;
         const TailLevel& Cc = A.lev[l + 1];
         for (long long C = tid; C < Cc.g.n; C += nth) {
             int I, Jc, Kc;
             tpb_ijk(C, Cc.g.nx, Cc.g.ny, I, Jc, Kc);
-            Cc.b[C] = restrict_cell<NS>(L.a, L.b, L.x, L.g, I, Jc, Kc);
+            Cc.b[C] = restrict_cell<NS>(L.a, L.b, cur, L.g, I, Jc, Kc);
         }
         bar();
     }
@@ -984,7 +1191,10 @@ __device__ __forceinline__ void cyc_down(const TailArgs& A, int l0, int l1, long
 template <int NS, class Barrier>
 __device__ __forceinline__ void cyc_coarsest(const TailArgs& A, long long tid, long long nth, Barrier& bar) {
     const TailLevel& L = A.lev[A.nlev - 1];
-    for (int s = 0; s < A.coarse_sweeps; s++) cyc_sweep<NS, false>(L, s == 0, nullptr, 0, 0, 0.0, tid, nth, bar);
+    if (NS == 7 && L.g.line)
+        cyc_line_smooth<false>(L, nullptr, L.x, A.coarse_sweeps, A.tile_sweeps, nullptr, 0, 0, 0.0, bar);
+    else
+        for (int s = 0; s < A.coarse_sweeps; s++) cyc_sweep<NS, false>(L, s == 0, nullptr, 0, 0, 0.0, tid, nth, bar);
 }
 
 // levels l1-1 down to l0: coarse correction (folded into the first post-smoothing sweep) + post-smoothing
@@ -994,15 +1204,19 @@ __device__ __forceinline__ void cyc_up(const TailArgs& A, int l1, int l0, long l
         const TailLevel& L = A.lev[l];
         const TailLevel& Cc = A.lev[l + 1];
         const LevGeom& f = L.g;
-        if (A.post > 0) {
+        const bool line = NS == 7 && f.line;
+        if (A.post > 0 && line) {
+            cyc_line_smooth<true>(L, L.xt, L.x, A.post, A.tile_sweeps, Cc.x, Cc.g.nx, Cc.g.ny, A.omega, bar);
+        } else if (A.post > 0) {
             cyc_sweep<NS, true>(L, false, Cc.x, Cc.g.nx, Cc.g.ny, A.omega, tid, nth, bar);
             for (int s = 1; s < A.post; s++) cyc_sweep<NS, false>(L, false, nullptr, 0, 0, 0.0, tid, nth, bar);
         } else {
+            const double* cur = line ? L.xt : L.x;
             for (long long c = tid; c < f.n; c += nth) {
                 int i, j, k;
                 tpb_ijk(c, f.nx, f.ny, i, j, k);
                 long long C = (i >> (f.cx - 1)) + (long long)Cc.g.nx * ((j >> (f.cy - 1)) + (long long)Cc.g.ny * (k >> (f.cz - 1)));
-                L.x[c] += A.omega * Cc.x[C];
+                L.x[c] = cur[c] + A.omega * Cc.x[C];
             }
             bar();
         }
@@ -1330,36 +1544,22 @@ long long gather_cells() {
 // slab; coarsening factors are agreed between the ranks (all-reduced coupling sums, the largest slab decides
 // whether the slab axis can still be halved) and coarsening stops at the gather level.  planes: owned planes of
 // every rank along the slab axis, updated to the last level built.
-// Columns per zebra-line tile: as many as give one cell per thread of a ZL_THREADS block (nz = 85: 12 columns,
-// 1020 cells), at most 32 (one warp per column in the solve phase), within the shared-memory budget of 3 arrays
-// [cpc][nz | 1]; 0 when not even one column fits.
+// dynamic shared memory of a hybrid line-smoother block on a level with nz planes
+inline size_t line_smem(int nz) {
+    int tx, ty;
+    line_tile_shape(nz, tx, ty);
+    return line_smem_doubles(nz, tx, ty) * sizeof(double);
+}
 constexpr size_t LINE_SMEM_BUDGET = 200 * 1024;
-inline int line_cpc(int nz, long long cols_per_colour, long long /*min_ctas*/) {
-    int cpc = std::max(1, std::min(32, ZL_THREADS / std::max(nz, 1)));
-    if (cols_per_colour > 0 && cpc > cols_per_colour) cpc = (int)cols_per_colour;
-    while (cpc > 1 && (size_t)3 * line_nzp(nz) * cpc * sizeof(double) > LINE_SMEM_BUDGET) cpc--;
-    if ((size_t)3 * line_nzp(nz) * cpc * sizeof(double) > LINE_SMEM_BUDGET) return 0;
-    return cpc;
-}
-inline int ilog2(int v) {
-    int l = 0;
-    while ((1 << l) < v) l++;
-    return l;
-}
-// threads of a zebra-line block: one per cell of the tile, whole warps, at most ZL_THREADS
-inline unsigned line_threads(int nz, int cpc) {
-    const long long t = ((long long)nz * cpc + 31) / 32 * 32;
-    return (unsigned)std::min<long long>(t, ZL_THREADS);
-}
-inline size_t line_smem(int nz, int cpc) { return (size_t)3 * line_nzp(nz) * cpc * sizeof(double); }
 
 template <int NS>
 void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int nz0, bool dist, std::vector<int>& planes) {
     PcState* pc = h->pc;
     const tpb_solver_opts& o = h->opts;
-    // zebra z-line smoothing on every level of a 3-D hierarchy (z is then never coarsened); falls back to the point
-    // smoother when a single column does not fit into shared memory
-    const bool line = NS == 7 && o.mg_smoother == TPB_MG_ZLINE && nz0 > 1 && line_cpc(nz0, 1, 0) > 0;
+    // z-line smoothing on every level of a 3-D hierarchy (z is then never coarsened); falls back to the point smoother
+    // when a one-column tile is more than a block's threads (LS_CPT cells each) or shared memory can hold
+    const bool line = NS == 7 && o.mg_smoother == TPB_MG_ZLINE && nz0 > 1 && nz0 <= LS_CPT * LS_THREADS &&
+                      line_smem(nz0) <= LINE_SMEM_BUDGET;
     // geometry of level 0 never changes between set-ups, and the coarsening schedule is recomputed from
     // the operator each time (as hypre's set-up is, preconditioners.py:878), so levels are re-allocated
     // only when their shape changes
@@ -1385,7 +1585,7 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
         L.line = line;
         if (line && L.fac_cap < L.cap) {
             tpb_dfree(L.fac);
-            L.fac = tpb_dalloc<double>((size_t)3 * L.cap);
+            L.fac = tpb_dalloc<double>((size_t)6 * L.cap);
             L.fac_cap = L.cap;
         }
         L.x = L.x_own;
@@ -1543,31 +1743,43 @@ void want_smem(K kernel, size_t bytes) {
     done.push_back({(const void*)kernel, bytes});
 }
 
-// one smoothing sweep = two colour passes: zebra z-line on line-smoothed levels, red-black points otherwise
+// `nsw` sweeps of the hybrid line smoother on a level: one launch per group of mg_tile_sweeps sweeps, out of place
+// (xin == nullptr: zero guess; coarse != nullptr: the first group reads xin + omega P coarse->x); buffer rotation as in
+// oracle/cport mg_line_smooth
+void mg_line_smooth(tpb_handle_s* h, const MgLevel& L, const double* xin, double* xout, int nsw,
+                    const MgLevel* coarse = nullptr, double omega = 0.0) {
+    LevGeom g = lg(L);
+    int group = h->opts.mg_tile_sweeps;
+    if (group <= 0 || group > nsw) group = nsw;
+    const int ncalls = (nsw + group - 1) / group;
+    int tx, ty;
+    line_tile_shape(L.nz, tx, ty);
+    const unsigned grid = (unsigned)(((L.nx + tx - 1) / tx) * ((L.ny + ty - 1) / ty));
+    const size_t smem = line_smem(L.nz);
+    const double* in = xin;
+    int left = nsw;
+    for (int c = 0; c < ncalls; c++) {
+        double* out = (c == ncalls - 1) ? xout : (((ncalls - 1 - c) & 1) ? L.xs0() : L.xs1());
+        const int sw = std::min(left, group);
+        if (coarse && c == 0) {
+            want_smem(line_smooth_kernel<true>, smem);
+            launch_pdl_smem(line_smooth_kernel<true>, grid, LS_THREADS, smem, h->stream, L.a, L.fac, L.b, in, out, g, coarse->x,
+                            coarse->nx, coarse->ny, omega, sw, tx, ty);
+        } else {
+            want_smem(line_smooth_kernel<false>, smem);
+            launch_pdl_smem(line_smooth_kernel<false>, grid, LS_THREADS, smem, h->stream, L.a, L.fac, L.b, in, out, g, nullptr,
+                            0, 0, 0.0, sw, tx, ty);
+        }
+        h->launches++;
+        left -= sw;
+        in = out;
+    }
+}
+
+// one red-black point Gauss-Seidel sweep = two colour passes
 template <int NS>
 void mg_rbgs(tpb_handle_s* h, const MgLevel& L, bool zero_guess, const MgLevel* coarse = nullptr, double omega = 0.0) {
     LevGeom g = lg(L);
-    if (L.line) {
-        const long long ncol = (long long)L.ny * ((L.nx + 1) >> 1);
-        const int cpc = line_cpc(L.nz, ncol, 2 * 148);
-        const int l2 = ilog2(cpc);
-        const size_t smem = line_smem(L.nz, cpc);
-        const unsigned grid = nblk(ncol, cpc);
-        const unsigned zt = line_threads(L.nz, cpc);
-        for (int col = 0; col < 2; col++) {
-            if (coarse && col == 0) {
-                want_smem(zline_kernel<true>, smem);
-                launch_pdl_smem(zline_kernel<true>, grid, zt, smem, h->stream, L.a, L.fac, L.b, L.x, g, col, 0, coarse->x,
-                                coarse->nx, coarse->ny, omega, cpc, l2);
-            } else {
-                want_smem(zline_kernel<false>, smem);
-                launch_pdl_smem(zline_kernel<false>, grid, zt, smem, h->stream, L.a, L.fac, L.b, L.x, g, col,
-                                (zero_guess && col == 0) ? 1 : 0, nullptr, 0, 0, 0.0, cpc, l2);
-            }
-            h->launches++;
-        }
-        return;
-    }
     long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
     for (int col = 0; col < 2; col++) {
         if (coarse && col == 0)
@@ -1588,7 +1800,7 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     const int coarse = m.last_sweeps > 0 ? m.last_sweeps : coarse_opt;
     const bool dist = m.glob != nullptr && !m.skip_glob;   // the last level is the gather level: smoothed as level 0 of m.glob
     const int last = m.nlev - 1;
-    // level zones: [0, lcoop) one kernel per colour pass, [ltail, last] inside one CTA (levels <= TAIL_CELLS)
+    // level zones: [0, lcoop) one kernel per smoothing pass, [ltail, last] inside one CTA (levels <= TAIL_CELLS)
     int ltail = m.nlev;
     while (ltail > 0 && m.lev[ltail - 1].n <= TAIL_CELLS) ltail--;
     const int lcoop = std::min(ltail, dist ? last : m.nlev);
@@ -1597,23 +1809,27 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         TailArgs A;
         A.nlev = mm.nlev - l0;
         for (int l = l0; l < mm.nlev; l++) {
-            A.lev[l - l0].g = lg(mm.lev[l]);
-            A.lev[l - l0].a = mm.lev[l].a;
-            A.lev[l - l0].x = mm.lev[l].x;
-            A.lev[l - l0].b = mm.lev[l].b;
-            A.lev[l - l0].fac = mm.lev[l].fac;
-            A.lev[l - l0].cpc = 1;
-            A.lev[l - l0].lg2 = 0;
-            if (mm.lev[l].line) {
-                const int cpc = line_cpc(mm.lev[l].nz, (long long)mm.lev[l].ny * ((mm.lev[l].nx + 1) >> 1), 0);
-                A.lev[l - l0].cpc = cpc;
-                A.lev[l - l0].lg2 = ilog2(cpc);
-                tail_smem = std::max(tail_smem, line_smem(mm.lev[l].nz, cpc));
+            TailLevel& T = A.lev[l - l0];
+            const MgLevel& L = mm.lev[l];
+            T.g = lg(L);
+            T.a = L.a;
+            T.x = L.x;
+            T.b = L.b;
+            T.fac = L.fac;
+            T.xt = T.xs0 = T.xs1 = nullptr;
+            T.tx = T.ty = 1;
+            if (L.line) {
+                T.xt = L.xt();
+                T.xs0 = L.xs0();
+                T.xs1 = L.xs1();
+                line_tile_shape(L.nz, T.tx, T.ty);
+                tail_smem = std::max(tail_smem, line_smem(L.nz));
             }
         }
         A.pre = pre;
         A.post = o.mg_post;
         A.coarse_sweeps = mm.last_sweeps > 0 ? mm.last_sweeps : coarse_opt;
+        A.tile_sweeps = o.mg_tile_sweeps;
         A.omega = o.mg_overcorrection;
         return A;
     };
@@ -1621,12 +1837,21 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     for (int l = 0; l < lcoop; l++) {
         MgLevel& L = m.lev[l];
         if (!dist && l == last) {
-            for (int s = 0; s < coarse; s++) mg_rbgs<NS>(h, L, s == 0);
+            if (L.line)
+                mg_line_smooth(h, L, nullptr, L.x, coarse);
+            else
+                for (int s = 0; s < coarse; s++) mg_rbgs<NS>(h, L, s == 0);
             break;
         }
-        for (int s = 0; s < pre; s++) mg_rbgs<NS>(h, L, s == 0);
+        if (L.line)
+            mg_line_smooth(h, L, nullptr, L.xt(), pre);
+        else
+            for (int s = 0; s < pre; s++) mg_rbgs<NS>(h, L, s == 0);
         MgLevel& Cc = m.lev[l + 1];
-        launch_pdl(restrict_kernel<NS>, nblk(Cc.n * 8, 256), 256, h->stream, L.a, L.b, L.x, lg(L), lg(Cc), Cc.b);
+        if (NS == 7 && L.line && L.cz == 1)
+            launch_pdl(restrict_line_kernel, nblk(Cc.n, 256), 256, h->stream, L.a, L.b, L.xt(), lg(L), lg(Cc), Cc.b);
+        else
+            launch_pdl(restrict_kernel<NS>, nblk(Cc.n * 8, 256), 256, h->stream, L.a, L.b, L.line ? L.xt() : L.x, lg(L), lg(Cc), Cc.b);
         h->launches++;
     }
     if (!dist) {
@@ -1672,11 +1897,16 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
         MgLevel& L = m.lev[l];
         MgLevel& Cc = m.lev[l + 1];
         if (o.mg_post > 0) {
-            // coarse correction folded into the first post-smoothing sweep (see rbgs_cell)
-            mg_rbgs<NS>(h, L, false, &Cc, o.mg_overcorrection);
-            for (int s = 1; s < o.mg_post; s++) mg_rbgs<NS>(h, L, false);
+            // coarse correction folded into the first post-smoothing pass (see rbgs_cell / line_tile_smooth)
+            if (L.line) {
+                mg_line_smooth(h, L, L.xt(), L.x, o.mg_post, &Cc, o.mg_overcorrection);
+            } else {
+                mg_rbgs<NS>(h, L, false, &Cc, o.mg_overcorrection);
+                for (int s = 1; s < o.mg_post; s++) mg_rbgs<NS>(h, L, false);
+            }
         } else {
-            prolong_add_kernel<<<nblk(L.n, 256), 256, 0, h->stream>>>(Cc.x, lg(L), lg(Cc), o.mg_overcorrection, L.x);
+            prolong_add_kernel<<<nblk(L.n, 256), 256, 0, h->stream>>>(Cc.x, lg(L), lg(Cc), o.mg_overcorrection,
+                                                                    L.line ? L.xt() : L.x, L.x);
             h->launches++;
         }
     }
@@ -1993,6 +2223,40 @@ void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double
     static const bool want = !(getenv("TPB_GRAPH") && atoi(getenv("TPB_GRAPH")) == 0);
     const tpb_solver_opts& o = h->opts;
     const bool any = o.stage1 != TPB_S1_NONE || o.stage2 != TPB_S2_NONE;
+    // The captured application only depends on pointers, level shapes and sweep counts - not on the operator values.
+    // When none of them changed since the last set-up (the usual case from one Newton iteration to the next: the
+    // coarsening schedule rarely moves), the executable graphs are kept as they are.
+    std::vector<long long> sig;
+    auto sig_hier = [&](const MgHier& m, auto&& self) -> void {
+        sig.push_back(m.nlev);
+        sig.push_back(m.last_sweeps);
+        sig.push_back(m.skip_glob ? 1 : 0);
+        for (int l = 0; l < m.nlev; l++) {
+            const MgLevel& L = m.lev[l];
+            for (long long v : {(long long)L.nx, (long long)L.ny, (long long)L.nz, (long long)L.cx, (long long)L.cy,
+                                (long long)L.cz, (long long)L.line, (long long)(intptr_t)L.a, (long long)(intptr_t)L.x,
+                                (long long)(intptr_t)L.b, (long long)(intptr_t)L.fac, L.fac_cap})
+                sig.push_back(v);
+        }
+        for (long long v : m.gcnt) sig.push_back(v);
+        sig.push_back(m.glob ? 1 : 0);
+        if (m.glob) self(*m.glob, self);
+    };
+    sig_hier(pc->mg_p, sig_hier);
+    sig_hier(pc->mg_T, sig_hier);
+    sig.push_back((long long)(intptr_t)J);
+    {
+        const unsigned char* ob = reinterpret_cast<const unsigned char*>(&h->opts);
+        long long hsh = 1469598103934665603LL;
+        for (size_t q = 0; q < sizeof(h->opts); q++) hsh = (hsh ^ ob[q]) * 1099511628211LL;
+        sig.push_back(hsh);
+    }
+    static const bool keep_graph = !(getenv("TPB_GRAPH_KEEP") && atoi(getenv("TPB_GRAPH_KEEP")) == 0);
+    if (want && any && keep_graph && !pc->prog.empty() && sig == pc->graph_sig) {
+        pc->graph_ok = true;
+        return;
+    }
+    pc->graph_sig = sig;
     if (want && any) {
         const size_t nd = (size_t)h->nf * h->g.n;
         if (!pc->gx) pc->gx = tpb_dalloc<double>(nd);
@@ -2088,23 +2352,24 @@ void tpb_pc_stage2_apply_impl(tpb_handle_s* h, const double* r, double* z) {
 }
 const double* tpb_pc_weights_impl(tpb_handle_s* h, int f) { return h->pc ? h->pc->w[f] : nullptr; }
 
-// one colour pass of the fine-level pressure smoother on its own (bench.py roofline of the dominant kernel);
-// returns the number of cells the pass updates
+// one smoothing launch of the fine-level pressure smoother on its own (bench.py roofline of the dominant kernel):
+// a group of mg_tile_sweeps sweeps of the hybrid line smoother, or one colour pass of the point smoother; returns the
+// number of cells it updates
 long long tpb_pc_rbgs_pass_impl(tpb_handle_s* h, int col) {
     TPB_REQUIRE(h->pc && h->pc->ready && h->pc->mg_p.nlev > 0, TPB_ERR_STATE, "pressure multigrid not set up");
     const MgLevel& L = h->pc->mg_p.lev[0];
     LevGeom g = lg(L);
     if (L.line) {
-        const long long ncol = (long long)L.ny * ((L.nx + 1) >> 1);
-        const int cpc = line_cpc(L.nz, ncol, 2 * 148);
-        const size_t smem = line_smem(L.nz, cpc);
-        want_smem(zline_kernel<false>, smem);
-        launch_pdl_smem(zline_kernel<false>, nblk(ncol, cpc), line_threads(L.nz, cpc), smem, h->stream, L.a, L.fac, L.b, L.x, g, col, 0,
-                        nullptr, 0, 0, 0.0, cpc, ilog2(cpc));
+        const int group = h->opts.mg_tile_sweeps > 0 ? h->opts.mg_tile_sweeps : std::max(1, h->opts.mg_pre);
+        int tx, ty;
+        line_tile_shape(L.nz, tx, ty);
+        const unsigned grid = (unsigned)(((L.nx + tx - 1) / tx) * ((L.ny + ty - 1) / ty));
+        const size_t smem = line_smem(L.nz);
+        want_smem(line_smooth_kernel<false>, smem);
+        launch_pdl_smem(line_smooth_kernel<false>, grid, LS_THREADS, smem, h->stream, L.a, L.fac, L.b, L.xs0(), L.xs1(), g,
+                        nullptr, 0, 0, 0.0, group, tx, ty);
         h->launches++;
-        long long cols = 0;   // columns of this colour
-        for (int j = 0; j < L.ny; j++) cols += (L.nx + 1 - ((col + j) & 1)) / 2;
-        return cols * L.nz;
+        return L.n;
     }
     long long threads = (long long)L.ny * L.nz * ((L.nx + 1) >> 1);
     if (h->ns == 7)

@@ -52,7 +52,7 @@ if "c3" in which:
     for pc in ("pc_cptr", "pc_cpr_TI"):
         run("C3", geo, case, prm, 2, pc, end=0.004, maxdt=0.002, small_dt_start=True, dt_init_fact=2 ** -4)
 if "c4" in which:
-    N = 40
+    N = int(os.environ.get("C4N", "40"))
     prm = params(rate=1e-7, T_inj=373.15, S_o=0.9)
     geo = G.HomogeneousBoxGeo(N, N, N, prm, 50.0, 50.0, 50.0)
     case = CS.HeaterCase(prm, geo, heater_points=heater_points(50.0))
