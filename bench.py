@@ -12,8 +12,11 @@ workload SPE10-shaped synthetic 60x220x85 (x N ranks in z for weak scaling), Two
          'default' (Peaceman, rate 2e-4, S_o 0.9), solver_parameters 'pc_cptr'.
 
 `--impl reference` times the CPU restatement of the same path (oracle/cport, C + OpenMP, all host
-threads) on a bounded sample of the same workload; the reference itself (Firedrake/PETSc/hypre) cannot
-be installed in this image.
+threads): at --gpus 1 on the SAME configuration (the full 60x220x85 grid, same steps), at --gpus N > 1 on
+a bounded sample (the top 17 layers) because the N-times-stacked grid would take N times as long; the
+line says which (`config.same_config`).  The reference itself (Firedrake/PETSc/hypre) cannot be installed
+in this image.  The port's own assembly / SpMV GB/s are reported against a STREAM triad
+measured in the same run (`cpu_baseline.roofline`).
 """
 import argparse
 import json
@@ -171,22 +174,49 @@ def cpu_run(nz_layers, steps, warmup, verbose=False):
     res = run_time_loop(newton, NpOps(), u, uo, max_steps=steps, dt0=dt0, **kw)
     sec = time.perf_counter() - t0
     val = n * res.total_nits / sec / 1e6
-    return val, sec, res, eng.num_threads(), n
+    # the port's own roofline: its assembly and SpMV (algorithmic bytes of SURVEY 8d) against the host's STREAM triad
+    roof = None
+    try:
+        dt = res.dt_vec[-1]
+        F, J = eng.assemble(u, uo, dt)
+        x = np.random.default_rng(0).standard_normal(u.shape)
+        ta, ts = [], []
+        for _ in range(3):
+            t1 = time.perf_counter()
+            eng.assemble(u, uo, dt)
+            ta.append(time.perf_counter() - t1)
+            t1 = time.perf_counter()
+            eng.spmv(J, x)
+            ts.append(time.perf_counter() - t1)
+        stream = cport.stream_triad_gbs(40_000_000, 5)
+        ga, gs = BYTES["assemble_FJ"] * n / min(ta) / 1e9, BYTES["spmv"] * n / min(ts) / 1e9
+        roof = {"stream_triad_gbs": stream, "assembly_gbs": ga, "assembly_frac": ga / stream, "spmv_gbs": gs,
+                "spmv_frac": gs / stream, "note": "algorithmic bytes (608 / 552 B per cell) / best of 3, Python call overhead and "
+                "the output allocation included; STREAM triad over 3 x 320 MB, best of 5, same threads"}
+    except Exception as e:   # the roofline is a side note of the baseline, never a reason to lose the line
+        roof = {"error": repr(e)}
+    return val, sec, res, eng.num_threads(), n, roof
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, sec, res, threads, n = cpu_run(CPU_SAMPLE_NZ, args.steps, args.warmup)
-    sample = ("top %d of %d layers (60x220x%d = %d cells) of the same synthetic SPE10 field, same wells, physics, "
-              "option set and time loop; CPU restatement oracle/cport (C+OpenMP), %d steps after %d warm-up"
-              % (CPU_SAMPLE_NZ, NZ, CPU_SAMPLE_NZ, n, args.steps, args.warmup))
+    same = args.gpus <= 1 and not args.cpu_sample
+    nzl = NZ if same else CPU_SAMPLE_NZ
+    val, sec, res, threads, n, roof = cpu_run(nzl, args.steps, args.warmup)
+    if same:
+        sample = ("the whole workload: 60x220x%d = %d cells, same field, wells, physics, option set and time loop; CPU restatement "
+                  "oracle/cport (C+OpenMP), %d steps after %d warm-up" % (NZ, n, args.steps, args.warmup))
+    else:
+        sample = ("top %d of %d layers (60x220x%d = %d cells) of the same synthetic SPE10 field, same wells, physics, "
+                  "option set and time loop; CPU restatement oracle/cport (C+OpenMP), %d steps after %d warm-up"
+                  % (CPU_SAMPLE_NZ, NZ, CPU_SAMPLE_NZ, n, args.steps, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3 / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(NZ, 1), "sample": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(NZ, 1), "sample": sample, "same_config": same, "cells": n},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "roofline": roof},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "nits": res.nits_vec, "lits": res.lits_vec,
             "note": "Firedrake/PETSc/hypre are not installable here; this is the CPU restatement, not the reference"}
@@ -319,17 +349,27 @@ def run_b200(args):
     eng.assemble(u, uo, res.dt_vec[-1], F=F, J=J)
     eng.pc_setup(J, u, res.dt_vec[-1])
     roof = {}
-    # per-launch DRAM traffic from the committed `ncu --set full` captures (profiles/r1_ncu_full_summary.md)
-    traffic = {"spmv": 597.0e6 if n_loc == 1122000 else None, "assemble_FJ": 715.5e6 if n_loc == 1122000 else None, "rbgs_fine": 83.1e6 if n_loc == 1122000 else None}
+    # per-launch DRAM traffic (dram__bytes_read + write of one `ncu --set full` capture of the same kernel at the same
+    # size): never measured inside this run - read from the committed capture summary, with its provenance
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    except Exception:
+        tr = {}
+    opt_now = eng.solver_opts()
+    group = opt_now["mg_tile_sweeps"] if opt_now["mg_tile_sweeps"] > 0 else opt_now["mg_pre"]
     for which, name, bpc, units in ((0, "assemble_FJ", BYTES["assemble_FJ"], n_loc), (2, "spmv", BYTES["spmv"], n_loc),
-                                    (3, "rbgs_fine", 80, n_loc // 2)):
+                                    (3, "line_smooth_fine", 88, n_loc)):
         t_ms = eng.time_kernel(which, u, uo, res.dt_vec[-1], F, J, x, y, reps=20)
         gbs = bpc * units / t_ms / 1e6
-        roof[name] = {"bound": "hbm", "achieved": gbs, "peak": pk, "unit": "GB/s", "frac": gbs / pk, "traffic": traffic[name],
-                      "ms_per_launch": t_ms, "bytes_per_unit": bpc, "units_per_launch": units, "peak_source": pk_how}
+        ent = tr.get(name, {}) if n_loc == 1122000 else {}
+        roof[name] = {"bound": "hbm", "achieved": gbs, "peak": pk, "unit": "GB/s", "frac": gbs / pk, "traffic": ent.get("bytes"),
+                      "traffic_from": ent.get("from"), "ms_per_launch": t_ms, "bytes_per_unit": bpc, "units_per_launch": units,
+                      "peak_source": pk_how}
     roof["assemble_FJ"]["note"] = "property pre-pass + flux kernel + source kernel (3 launches)"
-    roof["rbgs_fine"]["note"] = ("one colour pass of the fine-level pressure smoother: the kernel with the largest share of the step "
-                                 "(profiles/r1_launch_summary.md); 80 B per updated cell, half the cells per pass")
+    roof["line_smooth_fine"]["note"] = (
+        "one launch of the hybrid z-line smoother on the finest pressure level (%d sweeps per launch): the kernel with the largest "
+        "share of the step (profiles/r2_launch_summary.md).  88 B per cell = a1..a4 32 + three Thomas factors 24 + b 8 + x in 8 + x out "
+        "8 + the tile rims' re-reads ~8; the kernel is issue-bound, not HBM-bound (DESIGN.md)" % group)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -343,15 +383,16 @@ def run_b200(args):
             "failed_solves": res.failed_solves, "failed": res.failed, "host_wall_ms_per_step": wall * 1e3 / args.steps,
             "phase_ms": {"assemble": sum(s.t_assemble_ms for s in res.stats), "pc_setup": sum(s.t_pcsetup_ms for s in res.stats),
                          "ksp": sum(s.t_ksp_ms for s in res.stats)},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof["spmv"], "roofline_assembly": roof["assemble_FJ"],
-            "roofline_dominant_by_share": roof["rbgs_fine"]}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof["line_smooth_fine"],
+            "roofline_spmv": roof["spmv"], "roofline_assembly": roof["assemble_FJ"]}
     if e2e is not None:
         line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu:
-        cval, csec, cres, threads, cn = cpu_run(CPU_SAMPLE_NZ, 6, 2)
-        line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "top %d of %d layers (%d cells), 6 steps after 2 warm-up, oracle/cport C+OpenMP "
-                                          "restatement of the same path (%.1f s)" % (CPU_SAMPLE_NZ, NZ, cn, csec)}
+        cval, csec, cres, threads, cn, croof = cpu_run(CPU_SAMPLE_NZ, 6, 2)
+        line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": threads, "kind": "port", "roofline": croof,
+                                "sample": "bounded sample, NOT the same configuration: top %d of %d layers (%d cells), 6 steps "
+                                          "after 2 warm-up, oracle/cport C+OpenMP restatement of the same path (%.1f s); "
+                                          "`--impl reference` runs the whole grid" % (CPU_SAMPLE_NZ, NZ, cn, csec)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     eng.close()
@@ -366,6 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)     # dt from the small_dt_start phase up to ~0.1 day
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", action="store_true", help="--impl reference: the 17-layer sample also at --gpus 1")
     ap.add_argument("--scale", default="stack", choices=["stack", "refine"], help="how the grid grows with --gpus (weak scaling)")
     ap.add_argument("--mult", type=int, default=0, help="grid multiplier when it should differ from --gpus (experiments: "
                     "the N-rank problem on fewer ranks)")

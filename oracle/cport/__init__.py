@@ -107,8 +107,15 @@ def load():
     lib.tpc_mg_apply.argtypes = [vp, i, dp, dp]
     lib.tpc_stage2_apply.argtypes = [vp, dp, dp]
     lib.tpc_get_weights.argtypes = [vp, i, dp]
+    lib.tpc_stream_triad_gbs.argtypes = [C.c_long, i]
+    lib.tpc_stream_triad_gbs.restype = d
     _lib = lib
     return lib
+
+
+def stream_triad_gbs(n=40_000_000, reps=5):
+    """host STREAM triad bandwidth in GB/s with the threads the library currently uses (bench.py's CPU roofline)."""
+    return float(load().tpc_stream_triad_gbs(int(n), int(reps)))
 
 
 def default_opts(nphase):

@@ -1771,3 +1771,39 @@ int tpc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* Host memory bandwidth of the box the baseline runs on (STREAM triad a = b + s*c over three arrays of n doubles, best of
+ * reps, all threads; 24 bytes per element counted, write-allocate traffic not): the denominator bench.py reports the
+ * port's own assembly / SpMV GB/s against. */
+double tpc_stream_triad_gbs(long n, int reps) {
+    double* a = (double*)malloc(sizeof(double) * n);
+    double* b = (double*)malloc(sizeof(double) * n);
+    double* c = (double*)malloc(sizeof(double) * n);
+    if (!a || !b || !c) {
+        free(a);
+        free(b);
+        free(c);
+        return 0.0;
+    }
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n; i++) {
+        a[i] = 0.0;
+        b[i] = 1.0 + (double)(i & 7);
+        c[i] = 0.5;
+    }
+    double best = 0.0;
+    for (int r = 0; r < reps; r++) {
+        const double t0 = now_ms();
+#pragma omp parallel for schedule(static)
+        for (long i = 0; i < n; i++) a[i] = b[i] + 3.0 * c[i];
+        const double ms = now_ms() - t0;
+        const double gbs = 24.0 * (double)n / (ms * 1e6);
+        if (gbs > best) best = gbs;
+    }
+    volatile double sink = a[n / 2];
+    (void)sink;
+    free(a);
+    free(b);
+    free(c);
+    return best;
+}

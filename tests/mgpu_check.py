@@ -69,15 +69,16 @@ eng.close()
 from thermalporous_b200.model import TwoPhase, run_time_loop
 model = TwoPhase(geo, case, prm, end=0.002, maxdt=0.001, small_dt_start=True, dt_init_fact=2 ** -2,
                  solver_parameters="pc_cptr", verbosity=False, device=local)
+model.engine.set_solver_opts(snes_rtol=1e-11, snes_stol=1e-13, ksp_rtol=1e-10, snes_max_it=40)   # both sides converged tightly
 res = model.solve()
 class NpOps:
     def copy(self, d, s): d[...] = s
     def minmax(self, u, f): return float(u[f].min()), float(u[f].max())
     def clip(self, u, f, lo, hi): np.clip(u[f], lo, hi, out=u[f])
 # a Newton count at the tolerance edge steers the SPE10 dt heuristic, so the CPU run follows the dt sequence the
-# 2-rank run took (default tolerances on the GPU side, tight ones here -> agreement to the GPU run's accuracy)
+# slab run took; both sides are converged far below the default tolerances -> fields at the north_star's 1e-8
 o2, _, _ = O.resolve("pc_cptr", 2)
-o2.update(snes_rtol=1e-11, snes_stol=1e-13, **DD)
+o2.update(snes_rtol=1e-11, snes_stol=1e-13, ksp_rtol=1e-10, snes_max_it=40, **DD)
 cpu.set_solver_opts(**o2)
 uc2 = u0.copy()
 class RC: pass
@@ -87,7 +88,7 @@ for dt in res.dt_vec:
     rc.nits_vec.append(st2.nits)
     np.clip(uc2[2], 0.0, 1.0, out=uc2[2])
 em = max(rel(model.fields()[f], slab.take(uc2)[f]) for f in range(3))
-ok2 = res.failed_solves == 0 and abs(res.t - 0.002 * 86400.0) < 1e-6 and em < 1e-6
+ok2 = res.failed_solves == 0 and abs(res.t - 0.002 * 86400.0) < 1e-6 and em < 1e-8
 print("rank %d/%d: model.solve() %d steps nits %s (cpu %s) fields %.1e | %s" % (rank, world, len(res.dt_vec), res.nits_vec,
       rc.nits_vec, em, "OK" if ok2 else "FAIL"), flush=True)
 ok = ok and ok2

@@ -31,3 +31,16 @@ def test_two_slabs_reproduce_single_domain(gather, p2p):
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("| OK") == 4      # two checks (kernels + Newton, model.solve()) on two ranks
+
+
+def test_two_slabs_on_the_bench_workload_reproduce_single_domain():
+    """tests/mgpu_bench_check.py: the 2x stacked 60x220x85 bench workload on two slabs against the same grid as ONE domain
+    (fields 1e-8, no runaway Newton step)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "mgpu_bench_check.py"), "3"]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("| OK") == 2

@@ -125,6 +125,10 @@ class Engine:
             setattr(self.opts, k, v)
         self._chk(self.lib.tpb_set_solver_opts(self.h, C.byref(self.opts)))
 
+    def solver_opts(self):
+        """the solver options currently set, as a dict"""
+        return {name: getattr(self.opts, name) for name, _ in self.opts._fields_}
+
     def pc_setup(self, J, u, dt):
         u = self.tensor(u).reshape(self.nf, self.n)
         self._keep["pc"] = (J, u)   # the handle keeps raw pointers to both
