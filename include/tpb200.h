@@ -199,6 +199,9 @@ int tpb_newton_solve_host(tpb_handle h, double* u_host, const double* u_old_host
 /* out[0]=min S, out[1]=max S over field f of u */
 int tpb_field_minmax(tpb_handle h, const double* u, int f, double* out);
 int tpb_clip_field(tpb_handle h, double* u, int f, double lo, double hi);
+/* two-phase: total oil mass in the reservoir, sum over all ranks' cells of V phi S_o rho_o(p, T) - replaces
+ * assemble(phi*S_o*oil_rho(p,T)*dx), thermalmodel.py:190 */
+int tpb_oil_mass(tpb_handle h, const double* u, double* out);
 int tpb_dot(tpb_handle h, const double* x, const double* y, size_t n, double* out);
 
 /* ---- multi-GPU: slab partition; NCCL is loaded at run time (dlopen of libnccl.so.2) -------- */

@@ -59,7 +59,7 @@ SYMBOLS = [
     "tpb_create", "tpb_destroy", "tpb_last_error", "tpb_version", "tpb_set_field", "tpb_set_field_ghost",
     "tpb_set_sources", "tpb_assemble", "tpb_set_state_ghost", "tpb_jacobian_size", "tpb_nstencil", "tpb_spmv",
     "tpb_solver_defaults", "tpb_set_solver_opts", "tpb_pc_setup", "tpb_pc_apply", "tpb_ksp_solve",
-    "tpb_newton_solve", "tpb_newton_solve_host", "tpb_field_minmax", "tpb_clip_field", "tpb_dot",
+    "tpb_newton_solve", "tpb_newton_solve_host", "tpb_field_minmax", "tpb_clip_field", "tpb_oil_mass", "tpb_dot",
     "tpb_comm_init", "tpb_comm_unique_id", "tpb_exchange_static", "tpb_comm_peer_mode", "tpb_launch_count", "tpb_time_kernel",
     "tpb_stream", "tpb_sync", "tpb_pc_mg_nlevels", "tpb_pc_mg_level", "tpb_pc_mg_apply", "tpb_pc_stage2_apply",
     "tpb_pc_get_weights",
@@ -105,6 +105,7 @@ def load():
     lib.tpb_newton_solve.argtypes = [vp, dp, dp, d, C.POINTER(Stats)]
     lib.tpb_newton_solve_host.argtypes = [vp, dp, dp, d, C.POINTER(Stats)]
     lib.tpb_field_minmax.argtypes = [vp, dp, i, C.POINTER(d)]
+    lib.tpb_oil_mass.argtypes = [vp, dp, C.POINTER(d)]
     lib.tpb_clip_field.argtypes = [vp, dp, i, d, d]
     lib.tpb_dot.argtypes = [vp, dp, dp, C.c_size_t, C.POINTER(d)]
     lib.tpb_comm_init.argtypes = [vp, vp, i, i]

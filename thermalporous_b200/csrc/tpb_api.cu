@@ -9,6 +9,7 @@
 #include "tpb_internal.cuh"
 
 void tpb_minmax_impl(tpb_handle_s* h, size_t n, const double* x, double* out2);
+void tpb_oil_mass_impl(tpb_handle_s* h, const double* u);
 void tpb_clip_impl(tpb_handle_s* h, size_t n, double* x, double lo, double hi);
 void tpb_comm_init_impl(tpb_handle_s* h, const void* id128, int rank, int nranks);
 void tpb_comm_unique_id_impl(void* out128);
@@ -401,6 +402,18 @@ int tpb_newton_solve_host(tpb_handle h, double* u_host, const double* u_old_host
     TPB_CUDA(cudaMemcpyAsync(h->nw_uold, u_old_host, nd * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     tpb_newton_impl(h, h->nw_u, h->nw_uold, dt, stats);
     TPB_CUDA(cudaMemcpyAsync(u_host, h->nw_u, nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    TPB_CUDA(cudaStreamSynchronize(h->stream));
+    TPB_CATCH(h)
+}
+
+int tpb_oil_mass(tpb_handle h, const double* u, double* out) {
+    TPB_TRY(h)
+    TPB_REQUIRE(h && u && out, TPB_ERR_ARG, "null argument");
+    TPB_REQUIRE(h->nphase == 2, TPB_ERR_UNSUPPORTED, "oil mass is a two-phase diagnostic (thermalmodel.py:184-192)");
+    TPB_REQUIRE(h->fld_set[TPB_PHI], TPB_ERR_STATE, "porosity not set");
+    tpb_oil_mass_impl(h, u);
+    if (h->comm) tpb_allreduce_sum(h, h->red_out, 1);
+    TPB_CUDA(cudaMemcpyAsync(out, h->red_out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     TPB_CUDA(cudaStreamSynchronize(h->stream));
     TPB_CATCH(h)
 }

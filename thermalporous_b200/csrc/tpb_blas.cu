@@ -148,6 +148,37 @@ __global__ void minmax_kernel(size_t n, const double* __restrict__ x, double* __
         out[1] = b;
     }
 }
+// total oil mass of the slab: sum over cells of vol * phi * S_o * rho_o(p, T)  (thermalmodel.py:190); same
+// two-stage deterministic reduction as the dots
+__global__ void __launch_bounds__(RB) oil_mass_kernel(size_t n, const double* __restrict__ u, const double* __restrict__ phi,
+                                                      DevParams P, double vol, double* __restrict__ partial,
+                                                      unsigned int* __restrict__ counter, double* __restrict__ out) {
+    double acc = 0.0;
+    for (size_t i = (size_t)blockIdx.x * RB + threadIdx.x; i < n; i += (size_t)gridDim.x * RB)
+        acc += phi[i] * u[2 * n + i] * oil_rho_v(P, u[i], u[n + i]);
+    __shared__ double sm[RB / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    acc = warp_sum(acc);
+    if (lane == 0) sm[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < RB / 32; w++) v += sm[w];
+        partial[blockIdx.x] = v;
+        __threadfence();
+        unsigned int ticket = atomicInc(counter, gridDim.x - 1);
+        last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        __threadfence();
+        double v = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) v += partial[b];
+        v = warp_sum(v);
+        if (lane == 0) out[0] = v * vol;
+    }
+}
 __global__ void clip_kernel(size_t n, double* __restrict__ x, double lo, double hi) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         x[i] = fmin(fmax(x[i], lo), hi);
@@ -253,6 +284,14 @@ void tpb_minmax_impl(tpb_handle_s* h, size_t n, const double* x, double* out2) {
     TPB_CUDA(cudaStreamSynchronize(h->stream));
     out2[0] = h->red_host[0];
     out2[1] = h->red_host[1];
+}
+// this slab's oil mass -> h->red_out[0] (device); the caller reduces over the ranks and copies out
+void tpb_oil_mass_impl(tpb_handle_s* h, const double* u) {
+    ensure_red(h);
+    unsigned blocks = grid_for(h->g.n, RB);
+    oil_mass_kernel<<<blocks, RB, 0, h->stream>>>((size_t)h->g.n, u, h->fld[TPB_PHI], h->dp, h->g.vol, h->red_partial,
+                                                  h->red_counter, h->red_out);
+    h->launches++;
 }
 void tpb_clip_impl(tpb_handle_s* h, size_t n, double* x, double lo, double hi) {
     clip_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(n, x, lo, hi);

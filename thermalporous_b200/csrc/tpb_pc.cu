@@ -116,6 +116,13 @@ struct PcState {
     double *gx = nullptr, *gy = nullptr;
     bool graph_ok = false;
     std::vector<long long> graph_sig;   // what the captured application depends on (level shapes, buffers, sweep counts)
+    // programs of earlier set-ups, by signature: the coarsening schedule flips between a few variants from one Newton
+    // iteration to the next, and an executable graph stays valid as long as its signature comes back
+    struct Cached {
+        std::vector<long long> sig;
+        std::vector<Item> prog;
+    };
+    std::vector<Cached> cache;
 };
 
 namespace {
@@ -589,7 +596,6 @@ __global__ void __launch_bounds__(128) line_factor_kernel(const double* __restri
 // instructions per warp at 35 % issue utilisation), not memory-bound; 60x220x85: 57 / 71 us per launch.
 constexpr int LS_THREADS = 1024;
 constexpr int LS_CPT = 2;       // a tile holds at most LS_CPT * LS_THREADS cells (bounds its shared memory)
-__host__ __device__ __forceinline__ int line_nzp(int nz) { return nz | 1; }
 __host__ __device__ inline void line_tile_shape(int nz, int& tx, int& ty) {
     const int menu[3][2] = {{8, 3}, {4, 2}, {1, 1}};
     const int cols_max = nz > 0 ? (LS_CPT * LS_THREADS) / nz : 1;
@@ -1598,6 +1604,7 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
     };
     const int sax = h->g.dim - 1;   // slab axis
     int l = 0;
+    bool side_used = false;
     nw.lev[0] = take(0, nx0, ny0, nz0);
     if (nw.lev[0].own_a) tpb_dfree(nw.lev[0].a);
     nw.lev[0].a = a0;
@@ -1606,8 +1613,13 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
         MgLevel& L = nw.lev[l];
         L.cx = L.cy = L.cz = 1;
         if (line) {
-            line_factor_kernel<<<nblk((long long)L.nx * L.ny, 128), 128, 0, h->stream>>>(L.a, lg(L), L.fac);
+            // the column factorisations (one dependent chain of nz divisions per column: ~40 us whatever the level) run
+            // on the side stream beside the coarsening of the next levels; joined below
+            TPB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+            TPB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+            line_factor_kernel<<<nblk((long long)L.nx * L.ny, 128), 128, 0, h->stream2>>>(L.a, lg(L), L.fac);
             h->launches++;
+            side_used = true;
             if (L.nx == 1 && L.ny == 1) {   // a single column: the line solve is exact
                 nw.last_sweeps = 1;
                 break;
@@ -1673,6 +1685,10 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
         l++;
     }
     nw.nlev = l + 1;
+    if (side_used) {
+        TPB_CUDA(cudaEventRecord(h->ev_join, h->stream2));
+        TPB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    }
     mg_free_levels(old);
     m.nlev = nw.nlev;
     m.last_sweeps = nw.last_sweeps;
@@ -1801,8 +1817,18 @@ void mg_vcycle_t(tpb_handle_s* h, MgHier& m) {
     const bool dist = m.glob != nullptr && !m.skip_glob;   // the last level is the gather level: smoothed as level 0 of m.glob
     const int last = m.nlev - 1;
     // level zones: [0, lcoop) one kernel per smoothing pass, [ltail, last] inside one CTA (levels <= TAIL_CELLS)
+    // (line-smoothed levels only while they are a single tile: the one CTA walks a level's tiles one after the other,
+    // a launch of its own spreads them over the SMs)
+    static const int tail_tiles = getenv("TPB_MG_TAIL_TILES") ? atoi(getenv("TPB_MG_TAIL_TILES")) : 1;
+    auto in_tail = [&](const MgLevel& L) {
+        if (L.n > TAIL_CELLS) return false;
+        if (!L.line) return true;
+        int tx, ty;
+        line_tile_shape(L.nz, tx, ty);
+        return ((L.nx + tx - 1) / tx) * ((L.ny + ty - 1) / ty) <= tail_tiles;
+    };
     int ltail = m.nlev;
-    while (ltail > 0 && m.lev[ltail - 1].n <= TAIL_CELLS) ltail--;
+    while (ltail > 0 && in_tail(m.lev[ltail - 1])) ltail--;
     const int lcoop = std::min(ltail, dist ? last : m.nlev);
     size_t tail_smem = 0;   // dynamic shared memory the single-CTA kernels of this cycle need (line tiles)
     auto tail_args_of = [&](MgHier& mm, int l0) {
@@ -2131,6 +2157,9 @@ void tpb_pc_free(tpb_handle_s* h) {
     tpb_dfree(pc->strength);
     for (auto& it : pc->prog)
         if (it.g) cudaGraphExecDestroy(it.g);
+    for (auto& c : pc->cache)
+        for (auto& it : c.prog)
+            if (it.g) cudaGraphExecDestroy(it.g);
     for (auto g : pc->spare)
         if (g) cudaGraphExecDestroy(g);
     tpb_dfree(pc->gx);
@@ -2255,6 +2284,27 @@ void tpb_pc_setup_impl(tpb_handle_s* h, const double* J, const double* u, double
     if (want && any && keep_graph && !pc->prog.empty() && sig == pc->graph_sig) {
         pc->graph_ok = true;
         return;
+    }
+    if (want && any && keep_graph) {
+        // park the current program under its signature, take the one of the new signature if it was seen before
+        constexpr size_t CACHE_MAX = 6;
+        if (!pc->prog.empty()) {
+            pc->cache.insert(pc->cache.begin(), PcState::Cached{pc->graph_sig, std::move(pc->prog)});
+            pc->prog.clear();
+            while (pc->cache.size() > CACHE_MAX) {
+                for (auto& it : pc->cache.back().prog)
+                    if (it.g) cudaGraphExecDestroy(it.g);
+                pc->cache.pop_back();
+            }
+        }
+        for (size_t q = 0; q < pc->cache.size(); q++)
+            if (pc->cache[q].sig == sig) {
+                pc->prog = std::move(pc->cache[q].prog);
+                pc->cache.erase(pc->cache.begin() + q);
+                pc->graph_sig = sig;
+                pc->graph_ok = true;
+                return;
+            }
     }
     pc->graph_sig = sig;
     if (want && any) {

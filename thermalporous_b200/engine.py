@@ -177,6 +177,13 @@ class Engine:
         self._chk(self.lib.tpb_field_minmax(self.h, u.data_ptr(), f, out))
         return out[0], out[1]
 
+    def oil_mass(self, u):
+        """total oil mass over all ranks' slabs (two-phase), thermalmodel.py:190"""
+        out = C.c_double()
+        self._in()
+        self._chk(self.lib.tpb_oil_mass(self.h, u.data_ptr(), C.byref(out)))
+        return out.value
+
     def clip_field(self, u, f, lo, hi):
         self._in()
         self._chk(self.lib.tpb_clip_field(self.h, u.data_ptr(), f, float(lo), float(hi)))

@@ -51,7 +51,7 @@ class LoopResult:
 
 
 def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_fact, two_phase, i_S, spe10,
-                  verbose=False, log=print, max_steps=None, dt0=None, after_step=None):
+                  verbose=False, log=print, max_steps=None, dt0=None, after_step=None, oil_mass=False):
     """thermalmodel.py:97-348.  `newton(u, u_old, dt)` solves one step in place and returns an object with
     .nits .lits .reason (raises nothing); `ops` gives copy(dst, src), minmax(u, f) and clip(u, f, lo, hi).
     Times are in seconds except `end`/`maxdt` (days, as in the reference)."""
@@ -94,6 +94,10 @@ def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_
                 continue
             break
         if two_phase:                                            # :184-229
+            if oil_mass:                                         # :190-192 (a reduction over all ranks: every rank calls)
+                mass_o = ops.oil_mass(u)
+                if verbose:
+                    log("Total oil mass in reservoir: ", mass_o)
             eps = 1e-10
             smin, smax = ops.minmax(u, i_S)
             chop = (smax - 1.0 > eps) or (smin < -eps)
@@ -167,6 +171,9 @@ class _TorchOps:
 
     def minmax(self, u, f):
         return self.e.field_minmax(u, f)
+
+    def oil_mass(self, u):
+        return self.e.oil_mass(u)
 
     def clip(self, u, f, lo, hi):
         self.e.clip_field(u, f, lo, hi)
@@ -297,7 +304,7 @@ class ThermalModel:
                             end=self.end, maxdt=self.maxdt, small_dt_start=self.small_dt_start,
                             dt_init_fact=self.dt_init_fact, two_phase=self.nphase == 2, i_S=2,
                             spe10=self.geo.name.startswith("SPE10"), verbose=self.verbosity and self.rank == 0,
-                            max_steps=max_steps, after_step=after_step)
+                            max_steps=max_steps, after_step=after_step, oil_mass=self.verbosity and self.nphase == 2)
         if writer is not None:
             writer.close()
         self.result = res
