@@ -247,8 +247,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     prm = make_params()
-    refine = max(world, args.mult)
-    geo = make_geo(prm, NZ, refine, args.scale)      # global grid 60 x 220 x 85*world
+    refine = 1 if args.scale == "strong" else max(world, args.mult)
+    geo = make_geo(prm, NZ, refine, args.scale)      # global grid 60 x 220 x 85*world (strong: 60 x 220 x 85 whatever N)
     from thermalporous_b200.partition import Slab
     slab = Slab(geo, world, rank)
     if refine > 1 and args.scale == "stack":
@@ -371,7 +371,8 @@ def run_b200(args):
         "share of the step (profiles/r2_launch_summary.md).  88 B per cell = a1..a4 32 + three Thomas factors 24 + b 8 + x in 8 + x out "
         "8 + the tile rims' re-reads ~8; the kernel is issue-bound, not HBM-bound (DESIGN.md)" % group)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.scale == "strong" else "weak",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(geo.Nz, refine, args.scale), "cells": n_glob, "cells_per_gpu": n_loc,
                        "solver": desc, "l2": "working set per Newton step (Jacobian 565 MB + Krylov basis) exceeds the 126 MB L2; no flush needed",
@@ -408,7 +409,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-sample", action="store_true", help="--impl reference: the 17-layer sample also at --gpus 1")
-    ap.add_argument("--scale", default="stack", choices=["stack", "refine"], help="how the grid grows with --gpus (weak scaling)")
+    ap.add_argument("--scale", default="stack", choices=["stack", "refine", "strong"],
+                    help="how the grid grows with --gpus: stack / refine = weak scaling (one 85-layer slab per rank), strong = "
+                         "the same 60x220x85 grid cut into N z-slabs")
     ap.add_argument("--mult", type=int, default=0, help="grid multiplier when it should differ from --gpus (experiments: "
                     "the N-rank problem on fewer ranks)")
     ap.add_argument("--opt", action="append", default=[], help="solver option override key=value (experiments)")

@@ -1637,7 +1637,13 @@ void mg_coarsen_t(tpb_handle_s* h, MgHier& m, double* a0, int nx0, int ny0, int 
             nglob = L.n / dims[sax] * tot;
             dims[sax] = mx;
         }
-        const long long stop_at = dist ? std::max<long long>(gather_cells(), o.mg_min_cells) : o.mg_min_cells;
+        // Line-smoothed hierarchies on slabs do not gather (TPB_MG_GATHER_LINE=1 brings it back): z is never coarsened,
+        // so the gathered levels would be N x nz planes tall and walked by one CTA - measured on the stacked bench
+        // workload: identical Krylov counts with and without, 5 % (N=2) to 35 % (N=4) more time per iteration with.
+        // Every slab then ends on its own exactly solved column, the slabs stay coupled through the Krylov method only.
+        static const bool gather_line = getenv("TPB_MG_GATHER_LINE") && atoi(getenv("TPB_MG_GATHER_LINE")) != 0;
+        const bool gather = dist && (!line || gather_line);
+        const long long stop_at = gather ? std::max<long long>(gather_cells(), o.mg_min_cells) : o.mg_min_cells;
         if (nglob <= stop_at || nglob <= 1 || l == MAXLEV - 1) break;
         TPB_CUDA(cudaMemsetAsync(pc->strength, 0, 4 * sizeof(double), h->stream));
         unsigned blocks = std::min<unsigned>(nblk(L.n, 256), 1184u);
