@@ -151,15 +151,3 @@ def test_c4_two_phase_homogeneous_heaters():
 def prm_close(tmax, t_inj):
     return 300.0 < tmax <= t_inj + 1e-6
 
-
-def test_total_oil_mass_reduction():
-    """thermalmodel.py:190: assemble(phi * S_o * oil_rho(p, T) * dx) as a reduction kernel."""
-    from oracle import tp_oracle as orc
-    from tests.gpu_util import engine_from_problem, random_problem
-    pb, u, uo = random_problem(3, 2, (7, 9, 11), seed=3)
-    eng = engine_from_problem(pb)
-    got = eng.oil_mass(eng.tensor(u))
-    g = pb.grid
-    want = g.dx * g.dy * g.dz * float(np.sum(pb.phi * u[2] * orc.oil_rho(pb.prm, u[0], u[1])))
-    assert abs(got - want) <= 1e-13 * abs(want)
-    eng.close()

@@ -297,3 +297,16 @@ def test_snes_failure_is_reported_not_hidden():
     st = g.newton_solve(u, u.clone(), 86400.0)
     assert st.reason == -5       # SNES_DIVERGED_MAX_IT
     g.close()
+
+
+def test_total_oil_mass_reduction():
+    """thermalmodel.py:190: assemble(phi * S_o * oil_rho(p, T) * dx) as a reduction kernel."""
+    from oracle import tp_oracle as orc
+    from tests.gpu_util import engine_from_problem, random_problem
+    pb, u, uo = random_problem(3, 2, (7, 9, 11), seed=3)
+    eng = engine_from_problem(pb)
+    got = eng.oil_mass(eng.tensor(u))
+    g = pb.grid
+    want = g.dx * g.dy * g.dz * float(np.sum(pb.phi * u[2] * orc.oil_rho(pb.prm, u[0], u[1])))
+    assert abs(got - want) <= 1e-13 * abs(want)
+    eng.close()

@@ -21,6 +21,17 @@ try:
 except Exception as e:
     print('bench ERR', e); print(open('gpurun_out/${TAG}_bench_n$N.err').read()[-1500:])
 PY
+for mode in $EXTRA_SCALES; do
+  ( timeout 900 $TR --master-port 29515 bench.py --gpus $N --no-cpu --scale $mode 2>gpurun_out/${TAG}_bench_${mode}_n$N.err | tail -1 ) > gpurun_out/${TAG}_bench_${mode}_n$N.json
+  python - <<PY
+import json
+try:
+    d=json.loads(open('gpurun_out/${TAG}_bench_${mode}_n$N.json').read().strip().splitlines()[-1])
+    print('N=$N $mode value %.2f e2e %.2f ms/step %.1f nits %d lits %d failed %s phase %s'%(d['value'],d['e2e']['value'],d['ms_per_step'],sum(d['nits']),sum(d['lits']),d.get('failed'),d['phase_ms']))
+except Exception as e:
+    print('bench $mode ERR', e); print(open('gpurun_out/${TAG}_bench_${mode}_n$N.err').read()[-1500:])
+PY
+done
 if [ -n "$SAN" ]; then
   for tool in memcheck racecheck; do
     ( timeout 1500 $TR --master-port 29514 --no-python compute-sanitizer --tool $tool --print-limit 20 python tests/mgpu_check.py 2>&1 | grep -E "rank |ERROR SUMMARY|RACECHECK SUMMARY|Error|error|hazard" | cut -c1-260 | head -60 ) > gpurun_out/${TAG}_sanitizer_${tool}_n$N.log
