@@ -113,8 +113,12 @@ def run_time_loop(newton, ops, u, u_old, *, end, maxdt, small_dt_start, dt_init_
                     dt *= 0.5
                     ops.copy(u, u_old)
                     continue
+                smin = smax = None                               # the re-solved field's bounds are not known
                 break                                            # :218 (the re-check below it is dead code)
-            ops.clip(u, i_S, 0.0, 1.0)                           # :226-229
+            # :226-229 clips S_o to [0, 1] after every step; the bounds just computed say when that is the identity
+            # (one pass over the field saved - on host buffers that is 2 % of a step)
+            if smin is None or not (smin >= 0.0 and smax <= 1.0):
+                ops.clip(u, i_S, 0.0, 1.0)
         ops.copy(u_old, u)                                       # :296
         t += dt
         res.dt_vec.append(dt)
