@@ -356,3 +356,29 @@ def test_named_option_sets_equal_the_references_own_dictionaries():
         assert by_name == by_dict, key
     with pytest.raises(O.UnsupportedOption):
         O.resolve({"pc_type": "ilu", "ksp_rtoll": 1e-5}, 1)        # a typo is an error, not a dropped key
+
+
+def test_bench_reference_arm_line_keeps_the_contract(monkeypatch, capsys):
+    """bench.py --impl reference: one JSON line with the contract's keys, the CPU restatement's roofline, and an honest
+    same_config flag (true only for the whole grid at --gpus 1).  Run here on a 5-layer sample to stay fast."""
+    import argparse
+    import json
+    import bench
+    monkeypatch.setattr(bench, "CPU_SAMPLE_NZ", 5)
+    monkeypatch.delenv("RANK", raising=False)
+    args = argparse.Namespace(gpus=2, steps=1, warmup=1, cpu_sample=False)
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["config"]["same_config"] is False and line["config"]["cells"] == 60 * 220 * 5
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] == line["e2e"]["value"] > 0
+    assert cb["roofline"]["stream_triad_gbs"] > 0 and 0 < cb["roofline"]["spmv_frac"] < 2
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # only rank 0 prints under torchrun
+    monkeypatch.setenv("RANK", "1")
+    bench.run_reference(args)
+    assert capsys.readouterr().out == ""
