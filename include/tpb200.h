@@ -112,10 +112,7 @@ typedef struct {
     double mg_overcorrection; /* scaling of the piecewise-constant coarse correction */
     int mg_cycles;            /* V-cycles per application (pc_hypre_boomeramg_max_iter) */
     double mg_semi_theta;     /* an axis is coarsened on a level only if its mean coupling is at least
-                                 theta * the strongest axis' (0 = always coarsen every axis).  Default 0.25: on the
-                                 60x220x85 SPE10 case (Dy = Dx / 2: y couples 4x as strongly as x) it coarsens x and y
-                                 together from the first level - same Krylov counts as 0.5, one level and half of the
-                                 second level's cells fewer; 0 costs 20-35 % more iterations there */
+                                 theta * the strongest axis' (0 = always coarsen every axis) */
     int mg_full_below;        /* levels with at most this many cells coarsen every axis (0 = never) */
     double mg_dd_stop;        /* a level whose rows all satisfy sum|off-diagonals| <= mg_dd_stop * |diagonal| is the
                                  last one: it is solved by a few Gauss-Seidel sweeps (enough for a 1e-3 contraction, at

@@ -137,7 +137,7 @@ def default_opts(nphase):
     o.mg_min_cells = 8
     o.mg_overcorrection = 1.0
     o.mg_cycles = 1
-    o.mg_semi_theta = 0.25
+    o.mg_semi_theta = 0.5
     o.mg_full_below = 0
     o.mg_dd_stop = 0.1
     o.mg_coarse_scale = 0.5

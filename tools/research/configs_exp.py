@@ -26,8 +26,6 @@ def run(name, geo, case, prm, nphase, pc, **loop):
     eng.set_sources(CS.source_entries(case, prm, geo))
     opts, _, _ = O.resolve(pc, nphase)
     eng.set_solver_opts(**opts)
-    if os.environ.get("EXTRA_OPTS"):
-        eng.set_solver_opts(**{k: (float(v) if "." in v else int(v)) for k, v in (kv.split("=") for kv in os.environ["EXTRA_OPTS"].split(","))})
     n = geo.ncell
     u = np.stack([np.full(n, prm.p_ref), np.full(n, prm.T_prod)] + ([np.full(n, prm.S_o)] if nphase == 2 else []))
     t0 = time.time()

@@ -10,8 +10,6 @@ st = np.load(sys.argv[1]); nsteps = int(sys.argv[2])
 u, uo = st["u"].copy(), st["uo"].copy()
 nz = u.shape[1] // (60 * 220)
 eng, prm, geo = make_engine(nz)
-if os.environ.get('EXTRA_OPTS'):
-    eng.set_solver_opts(**{k: (float(v) if '.' in v else int(v)) for k, v in (kv.split('=') for kv in os.environ['EXTRA_OPTS'].split(','))})
 kw = dict(end=1e9, maxdt=bench.MAXDT, small_dt_start=True, dt_init_fact=bench.DT_INIT_FACT, two_phase=True, i_S=2, spe10=True)
 t0 = time.time()
 def newton(a, b, dt):
