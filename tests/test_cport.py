@@ -366,3 +366,33 @@ def test_hybrid_smoother_is_the_exact_zebra_sweep_when_the_level_is_one_tile():
         outs.append(eng.mg_apply(0, b))
         eng.close()
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+def test_two_stage_preconditioner_is_a_linear_operator():
+    """GMRES (single-phase sets, right preconditioning) needs a FIXED LINEAR preconditioner; zero-guess smoothing,
+    frozen tile rims, the folded coarse correction and the ILU sweeps must add up to one: M(a x + b y) = a M x + b M y."""
+    rng = np.random.default_rng(11)
+    for nphase, opts in ((2, dict(stage1=cport.S1_CPTR, decoup=1)), (1, dict(stage1=cport.S1_CPR, decoup=2)),
+                         (2, dict(stage1=cport.S1_CPTR, decoup=0, mg_tile_sweeps=1, mg_cycles=2))):
+        pb, u, uo = random_problem(3, nphase, (13, 10, 19), seed=2, spread=0.05)
+        eng = cport.engine_from_problem(pb)
+        eng.set_solver_opts(**opts)
+        F, J = eng.assemble(u, uo, 5000.0)
+        eng.pc_setup(J, u, 5000.0)
+        x, y = rng.standard_normal((2, pb.nf, pb.grid.n))
+        lhs = eng.pc_apply(0.7 * x - 2.5 * y)
+        rhs = 0.7 * eng.pc_apply(x) - 2.5 * eng.pc_apply(y)
+        assert np.abs(lhs - rhs).max() <= 1e-11 * np.abs(rhs).max()
+        eng.close()
+
+
+def test_hybrid_line_smoother_reduces_the_residual_of_a_pressure_block():
+    """one V-cycle from a zero guess must reduce the residual of the (row-repaired, M-matrix-like) pressure block"""
+    eng, u = _spe10_like_engine(19, 14, 23, mg_dd_stop=0.0)
+    F, J = eng.assemble(u, u, 86400.0)
+    eng.pc_setup(J, u, 86400.0)
+    a = eng.mg_level_op(0, 0)
+    b = np.random.default_rng(3).standard_normal(a.shape[1])
+    x = eng.mg_apply(0, b)
+    assert np.linalg.norm(b - _stencil_mv(a, x, 19, 14, 23)) < 0.5 * np.linalg.norm(b)
+    eng.close()
